@@ -193,6 +193,11 @@ int mpcv_closed_loop(mpcv_handle* h, const double* x_init, const double* pglob,
    the roofline denominator of bench.py. */
 int mpcv_fp64_peak(double* tflops, double* ms, void* stream);
 
+/* Optional per-problem latency capture: when `dev_ns` (device pointer, [B] int64) is non-NULL the
+   solve kernels stamp %globaltimer at each problem's entry and convergence exit and store the
+   difference in nanoseconds (the "p50 solve us" of BASELINE.json). NULL switches it off. */
+int mpcv_set_latency_buffer(mpcv_handle* h, long long* dev_ns);
+
 /* number of kernel launches issued through this handle since creation */
 int64_t mpcv_launch_count(const mpcv_handle* h);
 

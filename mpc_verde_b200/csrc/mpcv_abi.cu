@@ -1,0 +1,245 @@
+// mpcv_abi.cu — the C ABI of include/mpcv.h (model-independent part).
+// There is NO CPU fallback: every compute entry point fails with -ENODEV when no CUDA device is
+// usable; the per-model kernels live in mpcv_inst.cu.
+#include <cstdio>
+#include <cstring>
+
+#include "mpcv_host.h"
+
+using namespace mpcv;
+
+static thread_local std::string g_last_error;
+int mpcv_set_error(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+static const mpcv_model_vtable* vtable_of(int model) {
+  switch (model) {
+    case 0: return &mpcv_model_vtable_0;
+    case 1: return &mpcv_model_vtable_1;
+    case 2: return &mpcv_model_vtable_2;
+    case 3: return &mpcv_model_vtable_3;
+    case 4: return &mpcv_model_vtable_4;
+    case 5: return &mpcv_model_vtable_5;
+    case 6: return &mpcv_model_vtable_6;
+    default: return nullptr;
+  }
+}
+
+// FP64 FMA peak: 8 independent register-resident DFMA chains per thread
+__global__ void fp64_peak_kernel(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+         a7 = a0 + 7;
+  const double m = 1.0000001, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  out[(long)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+
+// ---------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------
+extern "C" {
+
+const char* mpcv_last_error(void) { return g_last_error.c_str(); }
+
+void mpcv_spec_defaults(mpcv_spec* s) {
+  std::memset(s, 0, sizeof(*s));
+  s->model = MPCV_MODEL_UNICYCLE_RK4_QUAD;   // multiple_shooting_casadi.py:29-45,75-82
+  s->shooting = MPCV_SHOOTING_MULTIPLE;
+  s->N = 10; s->M = 4; s->T = 0.2;
+  s->Q[0] = 1.0; s->Q[1] = 5.0; s->Q[2] = 0.1;
+  s->R[0] = 0.5; s->R[1] = 0.05;
+  s->tol = 1e-8; s->max_iter = 3000; s->max_soc = 4; s->mu_init = 0.1;
+  s->bound_push = 1e-2; s->bound_frac = 1e-2; s->bound_relax_factor = 1e-8;
+  s->nlp_scaling_max_gradient = 100.0;
+  s->dual_inf_tol = 1.0; s->constr_viol_tol = 1e-4; s->compl_inf_tol = 1e-4;
+}
+
+int mpcv_dims(const mpcv_spec* s, int32_t* nx, int32_t* nu, int32_t* n_var, int32_t* n_g, int32_t* n_p,
+              int32_t* npg, int32_t* nps) {
+  if (!s) return mpcv_set_error(-EINVAL, "null spec");
+  const mpcv_model_vtable* vt = vtable_of(s->model);
+  if (!vt) return mpcv_set_error(-EINVAL, "unsupported model id");
+  return vt->dims(s, nx, nu, n_var, n_g, n_p, npg, nps);
+}
+
+static int create_impl(mpcv_handle* h) {
+  const mpcv_model_vtable* vt = vtable_of(h->spec.model);
+  if (!vt) return mpcv_set_error(-EINVAL, "unsupported model id");
+  vt->fill(h);
+  return 0;
+}
+
+mpcv_handle* mpcv_create(const mpcv_spec* s) {
+  if (!s || s->N < 1 || s->N > 4096) { mpcv_set_error(-EINVAL, "bad spec"); return nullptr; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    mpcv_set_error(-ENODEV, "no CUDA device: mpc_verde_b200 has no CPU path");
+    return nullptr;
+  }
+  mpcv_handle* h = new mpcv_handle();
+  h->spec = *s;
+  h->single = s->shooting == MPCV_SHOOTING_SINGLE;
+  h->P = params_from_spec(*s);
+  if (create_impl(h) != 0) { delete h; return nullptr; }
+  cudaGetDevice(&h->device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, h->device) != cudaSuccess) { mpcv_set_error(-EIO, "cudaGetDeviceProperties"); delete h; return nullptr; }
+  h->sm_count = prop.multiProcessorCount;
+  h->max_smem_optin = prop.sharedMemPerBlockOptin;
+  h->layout = s->layout;
+  if (h->layout == MPCV_LAYOUT_AUTO)
+    h->layout = (!h->single && s->N >= 32) ? MPCV_LAYOUT_WARP : MPCV_LAYOUT_THREAD;
+  if (h->single) h->layout = MPCV_LAYOUT_THREAD;
+  if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    mpcv_set_error(-EIO, "cudaStreamCreate"); delete h; return nullptr;
+  }
+  return h;
+}
+
+void mpcv_destroy(mpcv_handle* h) {
+  if (!h) return;
+  if (h->slab) cudaFree(h->slab);
+  if (h->hpin) cudaFreeHost(h->hpin);
+  if (h->dstage) cudaFree(h->dstage);
+  if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  delete h;
+}
+
+int64_t mpcv_launch_count(const mpcv_handle* h) { return h ? h->launches : 0; }
+
+int mpcv_set_latency_buffer(mpcv_handle* h, long long* dev_ns) {
+  if (!h) return mpcv_set_error(-EINVAL, "null handle");
+  h->latency_ns = dev_ns;
+  return 0;
+}
+
+int mpcv_solve(mpcv_handle* h, const double* x0, const double* lbx, const double* ubx, const double* p,
+               double* x, double* f, double* g, double* lam_g, double* lam_x, int32_t* status, int32_t* iters,
+               int64_t B, void* stream) {
+  if (!h || !lbx || !ubx || !p) return mpcv_set_error(-EINVAL, "mpcv_solve: null argument");
+  SolveIO io{x0, lbx, ubx, p, x, f, g, lam_g, lam_x, status, iters, h->latency_ns};
+  cudaStream_t st = (cudaStream_t)stream;
+  return vtable_of(h->spec.model)->solve(h, io, (long)B, st);
+}
+
+int mpcv_rollout(mpcv_handle* h, const double* p, const double* U, double* X, double* q, int64_t B, void* stream) {
+  if (!h || !p || !U || !X) return mpcv_set_error(-EINVAL, "mpcv_rollout: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  return vtable_of(h->spec.model)->rollout(h, p, U, X, q, (long)B, st);
+}
+
+int mpcv_stage_derivs(mpcv_handle* h, const double* z, const double* pstage, const double* lam, double* xn,
+                      double* A, double* Bm, double* q, double* grad, double* H, int64_t B, void* stream) {
+  if (!h || !z || !lam) return mpcv_set_error(-EINVAL, "mpcv_stage_derivs: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  return vtable_of(h->spec.model)->derivs(h, z, pstage, lam, xn, A, Bm, q, grad, H, (long)B, st);
+}
+
+int mpcv_closed_loop(mpcv_handle* h, const double* x_init, const double* pglob, const double* ptraj,
+                     const double* lbx, const double* ubx, int32_t n_steps, int32_t warm_mode, double stop_radius,
+                     double* out_states, double* out_controls, int32_t* out_steps, int32_t* out_iters,
+                     int32_t* out_status, int64_t B, void* stream) {
+  if (!h || !x_init || !lbx || !ubx || !out_states || !out_controls)
+    return mpcv_set_error(-EINVAL, "mpcv_closed_loop: null argument");
+  if (h->nps > 0 && !ptraj) return mpcv_set_error(-EINVAL, "mpcv_closed_loop: ptraj required for this model");
+  if (h->npg > 0 && !pglob) return mpcv_set_error(-EINVAL, "mpcv_closed_loop: pglob required for this model");
+  LoopIO io{x_init, pglob, ptraj, lbx, ubx, out_states, out_controls, out_steps, out_iters, out_status,
+            n_steps, warm_mode, stop_radius};
+  cudaStream_t st = (cudaStream_t)stream;
+  return vtable_of(h->spec.model)->loop(h, io, (long)B, st);
+}
+
+// ---- host-pointer variant: H2D from pinned staging, solve, D2H, synchronise ---------------
+static int ensure_staging(mpcv_handle* h, size_t bytes) {
+  if (bytes > h->hpin_bytes) {
+    if (h->hpin) cudaFreeHost(h->hpin);
+    h->hpin = nullptr; h->hpin_bytes = 0;
+    CUDA_OK(cudaMallocHost(&h->hpin, bytes));
+    h->hpin_bytes = bytes;
+  }
+  if (bytes > h->dstage_bytes) {
+    if (h->dstage) cudaFree(h->dstage);
+    h->dstage = nullptr; h->dstage_bytes = 0;
+    CUDA_OK(cudaMalloc(&h->dstage, bytes));
+    h->dstage_bytes = bytes;
+  }
+  return 0;
+}
+
+int mpcv_solve_host(mpcv_handle* h, const double* x0, const double* lbx, const double* ubx, const double* p,
+                    double* x, double* f, double* g, double* lam_g, double* lam_x, int32_t* status,
+                    int32_t* iters, int64_t B) {
+  if (!h || !lbx || !ubx || !p) return mpcv_set_error(-EINVAL, "mpcv_solve_host: null argument");
+  const size_t n = h->n_var, ng = h->n_g, np = h->n_p;
+  auto al = [](size_t v) { return (v + 255) / 256 * 256; };
+  // input block: x0 | lbx | ubx | p ; output block: x | f | g | lam_g | lam_x | status | iters
+  const size_t o_x0 = 0, o_lb = o_x0 + al(x0 ? B * n * 8 : 0), o_ub = o_lb + al(n * 8), o_p = o_ub + al(n * 8);
+  const size_t in_bytes = o_p + al(B * np * 8);
+  const size_t o_x = in_bytes, o_f = o_x + al(B * n * 8), o_g = o_f + al(B * 8), o_lg = o_g + al(g ? B * ng * 8 : 0),
+               o_lx = o_lg + al(lam_g ? B * ng * 8 : 0), o_st = o_lx + al(lam_x ? B * n * 8 : 0), o_it = o_st + al(B * 4);
+  const size_t total = o_it + al(B * 4);
+  if (int rc = ensure_staging(h, total)) return rc;
+  char* hp = (char*)h->hpin;
+  char* dp = (char*)h->dstage;
+  if (x0) std::memcpy(hp + o_x0, x0, B * n * 8);
+  std::memcpy(hp + o_lb, lbx, n * 8);
+  std::memcpy(hp + o_ub, ubx, n * 8);
+  std::memcpy(hp + o_p, p, B * np * 8);
+  cudaStream_t st = h->own_stream;
+  CUDA_OK(cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, st));
+  int rc = mpcv_solve(h, x0 ? (const double*)(dp + o_x0) : nullptr, (const double*)(dp + o_lb), (const double*)(dp + o_ub),
+                      (const double*)(dp + o_p), (double*)(dp + o_x), (double*)(dp + o_f), g ? (double*)(dp + o_g) : nullptr,
+                      lam_g ? (double*)(dp + o_lg) : nullptr, lam_x ? (double*)(dp + o_lx) : nullptr,
+                      (int32_t*)(dp + o_st), (int32_t*)(dp + o_it), B, st);
+  if (rc) return rc;
+  CUDA_OK(cudaMemcpyAsync(hp + in_bytes, dp + in_bytes, total - in_bytes, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  if (x) std::memcpy(x, hp + o_x, B * n * 8);
+  if (f) std::memcpy(f, hp + o_f, B * 8);
+  if (g) std::memcpy(g, hp + o_g, B * ng * 8);
+  if (lam_g) std::memcpy(lam_g, hp + o_lg, B * ng * 8);
+  if (lam_x) std::memcpy(lam_x, hp + o_lx, B * n * 8);
+  if (status) std::memcpy(status, hp + o_st, B * 4);
+  if (iters) std::memcpy(iters, hp + o_it, B * 4);
+  return 0;
+}
+
+int mpcv_fp64_peak(double* tflops, double* ms, void* stream) {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return mpcv_set_error(-ENODEV, "no CUDA device");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaDeviceProp prop;
+  int dev = 0;
+  CUDA_OK(cudaGetDevice(&dev));
+  CUDA_OK(cudaGetDeviceProperties(&prop, dev));
+  const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 1 << 16;
+  double* out = nullptr;
+  CUDA_OK(cudaMalloc(&out, (size_t)threads * blocks * sizeof(double)));
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0));
+  CUDA_OK(cudaEventCreate(&e1));
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    CUDA_OK(cudaEventRecord(e0, st));
+    fp64_peak_kernel<<<blocks, threads, 0, st>>>(out, iters);
+    CUDA_OK(cudaEventRecord(e1, st));
+    CUDA_OK(cudaEventSynchronize(e1));
+    float t;
+    CUDA_OK(cudaEventElapsedTime(&t, e0, e1));
+    if (rep > 0 && t < best) best = t;
+  }
+  CUDA_OK(cudaGetLastError());
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  const double flops = 2.0 * 8.0 * iters * (double)threads * blocks;
+  if (tflops) *tflops = flops / (best * 1e-3) / 1e12;
+  if (ms) *ms = best;
+  return 0;
+}
+
+}  // extern "C"

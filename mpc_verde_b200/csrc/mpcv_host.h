@@ -1,0 +1,56 @@
+// mpcv_host.h — host-side handle and error plumbing shared by the ABI translation unit and the
+// per-model kernel instantiation units (one .cu object per model, built in parallel).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cerrno>
+#include <cstdint>
+#include <string>
+
+#include "mpcv_driver.cuh"
+#include "mpcv_params.h"
+
+int mpcv_set_error(int code, const std::string& msg);
+
+#define CUDA_OK(call)                                                                       \
+  do {                                                                                      \
+    cudaError_t e__ = (call);                                                               \
+    if (e__ != cudaSuccess)                                                                 \
+      return mpcv_set_error(-EIO, std::string(#call) + ": " + cudaGetErrorString(e__));     \
+  } while (0)
+
+struct mpcv_handle {
+  mpcv_spec spec;
+  mpcv::Params P;
+  mpcv::Layout L;
+  int nx, nu, n_var, n_g, n_p, npg, nps;
+  bool single;
+  int layout;            // resolved MPCV_LAYOUT_*
+  int device;
+  int sm_count;
+  size_t max_smem_optin;
+  double* slab = nullptr;   // thread-layout workspace
+  size_t slab_doubles = 0;
+  long slab_stride = 0;
+  // host-variant staging
+  void* hpin = nullptr; size_t hpin_bytes = 0;
+  void* dstage = nullptr; size_t dstage_bytes = 0;
+  cudaStream_t own_stream = nullptr;
+  long long* latency_ns = nullptr;   // optional device buffer [B]
+  int64_t launches = 0;
+};
+
+// per-model entry points (defined once per model in mpcv_inst.cu, -DMPCV_INST_MODEL=<id>)
+struct mpcv_model_vtable {
+  int (*dims)(const mpcv_spec*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*);
+  void (*fill)(mpcv_handle*);
+  int (*solve)(mpcv_handle*, const mpcv::SolveIO&, long, cudaStream_t);
+  int (*loop)(mpcv_handle*, const mpcv::LoopIO&, long, cudaStream_t);
+  int (*rollout)(mpcv_handle*, const double*, const double*, double*, double*, long, cudaStream_t);
+  int (*derivs)(mpcv_handle*, const double*, const double*, const double*, double*, double*, double*, double*,
+                double*, double*, long, cudaStream_t);
+};
+#define MPCV_DECLARE_MODEL(id) extern const mpcv_model_vtable mpcv_model_vtable_##id;
+MPCV_DECLARE_MODEL(0) MPCV_DECLARE_MODEL(1) MPCV_DECLARE_MODEL(2) MPCV_DECLARE_MODEL(3)
+MPCV_DECLARE_MODEL(4) MPCV_DECLARE_MODEL(5) MPCV_DECLARE_MODEL(6)

@@ -1,0 +1,1196 @@
+// mpcv_ipm.cuh — per-problem primal-dual interior-point solve with IPOPT semantics.
+//
+// Replaces the reference's `sol = solver(x0=,lbx=,ubx=,lbg=,ubg=,p=)` call
+// (Casadi/multiple_shooting_casadi.py:235-242, single_shooting_v1.py:174-181,
+// single_shooting_v2.py:212-219; `solver.solve()` in the MPCTools scripts).  IPOPT itself is a
+// third-party binary; the semantics followed here are those of Waechter & Biegler (2006)
+// with IPOPT 3.12 defaults: bound relaxation + push, z0 = 1, least-squares multiplier
+// initialisation, monotone barrier update, fraction-to-boundary, filter line search with
+// second-order correction, inertia correction by delta_w, the scaled E_0 <= tol test and
+// the final projection into the original bounds.
+//
+// KKT solve per problem:
+//   multiple shooting — block-tridiagonal Riccati recursion (backward sweep = adjoint sweep
+//     over the horizon, forward sweep = linearised rollout); "inertia correct" <=> every
+//     R + B'PB Cholesky succeeds.
+//   single shooting   — costate (adjoint) sweep for the exact condensed Hessian, dense
+//     Cholesky of H + Sigma + delta_w I.
+//
+// Execution shape: a group of LANES threads owns one problem.  LANES = 1 is the
+// thread-per-problem layout (workspace: structure-of-arrays in HBM, element i of problem b
+// at ws[i*stride + b], so a warp's accesses coalesce).  LANES = 32 is the warp-per-problem
+// layout (workspace in shared memory, stage-parallel derivative / trial evaluation, shuffle
+// reductions for the merit function, step norms and convergence tests; the sequential
+// Riccati sweeps run on lane 0).
+#pragma once
+
+#include "mpcv_models.cuh"
+
+namespace mpcv {
+
+constexpr double kInfBound = 1e19;   // IPOPT nlp_lower_bound_inf / nlp_upper_bound_inf
+
+// ---------------------------------------------------------------------------------------
+// group-of-lanes primitives
+// ---------------------------------------------------------------------------------------
+template <int LANES>
+struct Grp {
+  int lane;
+  unsigned mask;
+#if defined(__CUDACC__)
+  MPCV_D explicit Grp(int tid_in_warp) {
+    lane = tid_in_warp % LANES;
+    mask = LANES == 32 ? 0xffffffffu : (((1u << LANES) - 1u) << (tid_in_warp - lane));
+  }
+  MPCV_D void sync() const { if (LANES > 1) __syncwarp(mask); }
+  MPCV_D double sum(double v) const {
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) v += __shfl_xor_sync(mask, v, o, LANES);
+    return v;
+  }
+  MPCV_D double max(double v) const {
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(mask, v, o, LANES));
+    return v;
+  }
+  MPCV_D double min(double v) const {
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(mask, v, o, LANES));
+    return v;
+  }
+  MPCV_D int bcast(int v) const { return LANES > 1 ? __shfl_sync(mask, v, 0, LANES) : v; }
+#else
+  explicit Grp(int) : lane(0), mask(1u) { static_assert(LANES == 1, "host harness is single-lane"); }
+  void sync() const {}
+  double sum(double v) const { return v; }
+  double max(double v) const { return v; }
+  double min(double v) const { return v; }
+  int bcast(int v) const { return v; }
+#endif
+};
+
+// strided workspace view: element i lives at base[i*stride]
+struct WsStrided {
+  double* base;
+  long stride;
+  MPCV_HD double& operator[](int i) const { return base[(long)i * stride]; }
+};
+// contiguous workspace view (shared memory / host harness)
+struct WsDense {
+  double* base;
+  MPCV_HD double& operator[](int i) const { return base[i]; }
+};
+template <class WS>
+struct WsView {
+  WS ws;
+  int off;
+  MPCV_HD double operator[](int i) const { return ws[off + i]; }
+};
+
+// ---------------------------------------------------------------------------------------
+// workspace layout (in doubles) for one problem
+// ---------------------------------------------------------------------------------------
+struct Layout {
+  int n, m, N;
+  int w, lam, zl, zu, d, lamp, grad, c, ct, ab, hw, ric, pp, par, xs, hred, gam, tmp, total;
+};
+
+template <class Model, bool SINGLE>
+MPCV_HD Layout make_layout(int N) {
+  constexpr int NX = Model::NX, NU = Model::NU, NZ = NX + NU;
+  Layout L;
+  L.N = N;
+  L.n = SINGLE ? NU * N : NZ * N + NX;
+  L.m = SINGLE ? 0 : NX * (N + 1);
+  int o = 0;
+  L.w = o; o += L.n;
+  L.zl = o; o += L.n;
+  L.zu = o; o += L.n;
+  L.d = o; o += L.n;
+  L.grad = o; o += L.n;
+  L.lam = o; o += NX * (N + 1);
+  L.ab = o; o += N * (NX * NX + NX * NU);
+  L.hw = o; o += N * (NZ * (NZ + 1) / 2);
+  L.par = o; o += NX + Model::NPG + N * Model::NPS + 2;   // +2: alignment slack for bulk-staged stage params
+  L.lamp = L.c = L.ct = L.ric = L.pp = L.xs = L.hred = L.gam = L.tmp = 0;
+  if (SINGLE) {
+    L.xs = o; o += NX * (N + 1);
+    L.hred = o; o += (NU * N) * (NU * N + 1) / 2;
+    L.gam = o; o += NX * NU * N;
+    L.tmp = o; o += NZ * NU * N;
+  } else {
+    L.lamp = o; o += L.m;
+    L.c = o; o += L.m;
+    L.ct = o; o += L.m;
+    L.ric = o; o += N * (NU * NX + NU + NU * (NU + 1) / 2);
+    L.pp = o; o += (N + 1) * (NX * (NX + 1) / 2 + NX);
+  }
+  L.total = o;
+  return L;
+}
+
+struct SolveInfo {
+  int status, iters;
+  double f;       // unscaled objective
+  double df;      // objective scaling factor
+};
+
+MPCV_HD bool compare_le(double lhs, double rhs, double basval) {
+  return lhs - rhs <= 10.0 * 2.220446049250313e-16 * fabs(basval);
+}
+
+// ---------------------------------------------------------------------------------------
+template <class Model, bool SINGLE, int LANES, class WS>
+struct Ipm {
+  static constexpr int NX = Model::NX, NU = Model::NU, NZ = NX + NU;
+  static constexpr int NW = NZ * (NZ + 1) / 2, NPX = NX * (NX + 1) / 2, NF = NU * (NU + 1) / 2;
+  static constexpr int NAB = NX * NX + NX * NU, NRIC = NU * NX + NU + NF, NPP = NPX + NX;
+  static constexpr int FILTER_MAX = 8;
+
+  const Params& P;
+  const Layout& L;
+  WS ws;
+  Grp<LANES> g;
+  const double* lbx;   // [n] original bounds, shared by the batch
+  const double* ubx;
+  const int N;
+
+  int ps_base;         // offset of the stage parameters (shifted by 0/1 to match the source's 16-byte phase)
+  double df, mu, tau, f_curr;
+  double fil_phi[FILTER_MAX], fil_th[FILTER_MAX];
+  int nfil;
+
+  MPCV_D Ipm(const Params& p, const Layout& l, WS w, Grp<LANES> grp, const double* lb, const double* ub)
+      : P(p), L(l), ws(w), g(grp), lbx(lb), ubx(ub), N(l.N), ps_base(l.par + NX + Model::NPG), df(1.0), mu(0.1), tau(0.99), f_curr(0), nfil(0) {}
+
+  // ---- variable indexing ------------------------------------------------------------------
+  MPCV_D int ix(int k, int i) const { return k * NZ + i; }            // multiple shooting only
+  MPCV_D int iu(int k, int i) const { return SINGLE ? k * NU + i : k * NZ + NX + i; }
+  MPCV_D bool blocked(int k) const { return Model::HAS_UPREV && P.ntu > 0 && k >= P.ntu; }
+  // stage and component of variable i (multiple shooting)
+  MPCV_D bool var_is_blocked_u(int i) const {
+    if (!(Model::HAS_UPREV && P.ntu > 0)) return false;
+    const int k = SINGLE ? i / NU : i / NZ;
+    const int c = SINGLE ? i % NU : i % NZ - NX;
+    return c == 0 && k < N && k >= P.ntu;
+  }
+
+  struct Bnd { double lo, hi; bool hasl, hasu, fixed; };
+  MPCV_D Bnd bnd(int i) const {
+    Bnd b;
+    const double l = lbx[i], u = ubx[i];
+    b.hasl = l > -kInfBound;
+    b.hasu = u < kInfBound;
+    b.fixed = (b.hasl && b.hasu && l == u) || var_is_blocked_u(i);
+    if (b.fixed) b.hasl = b.hasu = false;
+    b.lo = b.hasl ? l - P.bound_relax * fmax(1.0, fabs(l)) : -INFINITY;
+    b.hi = b.hasu ? u + P.bound_relax * fmax(1.0, fabs(u)) : INFINITY;
+    return b;
+  }
+
+  MPCV_D WsView<WS> pg() const { return WsView<WS>{ws, L.par + NX}; }
+  MPCV_D WsView<WS> ps(int k) const { return WsView<WS>{ws, ps_base + k * Model::NPS}; }
+
+  // ---- stage access -----------------------------------------------------------------------
+  // load (x_k,u_k) of the vector at offset `off` shifted by alpha * (vector at offset `doff`)
+  MPCV_D void load_xu(int k, int off, double alpha, int doff, double* x, double* u) const {
+    if (!SINGLE) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        double v = ws[off + ix(k, i)];
+        if (alpha != 0.0) v += alpha * ws[doff + ix(k, i)];
+        x[i] = v;
+      }
+    }
+    if (k < N) {
+#pragma unroll
+      for (int i = 0; i < NU; ++i) {
+        double v = ws[off + iu(k, i)];
+        if (alpha != 0.0) v += alpha * ws[doff + iu(k, i)];
+        u[i] = v;
+      }
+      if (blocked(k)) u[0] = x[NX - 1];
+    }
+  }
+
+  // ---- derivatives at the current iterate ---------------------------------------------------
+  // fills ab, hw (when want_hess), grad (df * grad f), c (MS) and f_curr (scaled objective)
+  MPCV_DN void eval_derivatives(bool want_hess) {
+    if (SINGLE) {
+      eval_derivatives_single(want_hess);
+      return;
+    }
+    double fpart = 0.0;
+    for (int k = g.lane; k < N; k += LANES) {
+      double x[NX], u[NU], lamn[NX], xn[NX], A[NX * NX], B[NX * NU], q, gq[NZ], W[NW];
+      load_xu(k, L.w, 0.0, 0, x, u);
+#pragma unroll
+      for (int i = 0; i < NX; ++i) lamn[i] = ws[L.lam + (k + 1) * NX + i];
+      Model::der(P, x, u, pg(), ps(k), lamn, df, want_hess, xn, A, B, &q, gq, W);
+      if (blocked(k)) fold_blocked(A, B, gq, want_hess ? W : nullptr);
+      fpart += q;
+#pragma unroll
+      for (int i = 0; i < NX * NX; ++i) ws[L.ab + k * NAB + i] = A[i];
+#pragma unroll
+      for (int i = 0; i < NX * NU; ++i) ws[L.ab + k * NAB + NX * NX + i] = B[i];
+      if (want_hess) {
+#pragma unroll
+        for (int i = 0; i < NW; ++i) ws[L.hw + k * NW + i] = W[i];
+      }
+#pragma unroll
+      for (int i = 0; i < NX; ++i) ws[L.grad + ix(k, i)] = df * gq[i];
+#pragma unroll
+      for (int i = 0; i < NU; ++i) ws[L.grad + iu(k, i)] = df * gq[NX + i];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) ws[L.c + (k + 1) * NX + i] = xn[i] - ws[L.w + ix(k + 1, i)];
+    }
+    if (g.lane == 0) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        ws[L.c + i] = ws[L.par + i] - ws[L.w + ix(0, i)];   // xbar - X0 (MS:125-130)
+        ws[L.grad + ix(N, i)] = 0.0;                         // no terminal cost in the scripts
+      }
+    }
+    f_curr = df * g.sum(fpart);
+    g.sync();
+  }
+
+  // exact chain rule for a blocked stage: z = (x, u0 = x_{NX-1})
+  MPCV_D void fold_blocked(double* A, double* B, double* gq, double* W) const {
+    constexpr int j = NX - 1;
+#pragma unroll
+    for (int i = 0; i < NX; ++i) { A[i * NX + j] += B[i * NU]; B[i * NU] = 0.0; }
+    gq[j] += gq[NX]; gq[NX] = 0.0;
+    if (W) {
+      const double wuu = W[tri(NX, NX)], wuj = W[tri(NX, j)];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        if (i != j) W[tri(j, i)] += W[tri(NX, i)];
+        W[tri(NX, i)] = 0.0;
+      }
+      W[tri(j, j)] += 2.0 * wuj + wuu;
+      W[tri(NX, NX)] = 0.0;
+    }
+  }
+
+  // single shooting: rollout, costate sweep, exact Hessian blocks with the costates as multipliers
+  MPCV_DN void eval_derivatives_single(bool want_hess) {
+    if (g.lane == 0) {
+      double x[NX], u[NU], xn[NX], A[NX * NX], B[NX * NU], q, gq[NZ], W[NW], lamn[NX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) { x[i] = ws[L.par + i]; ws[L.xs + i] = x[i]; }
+      double fsum = 0.0;
+      // forward: states, A, B, cost gradient
+      for (int k = 0; k < N; ++k) {
+#pragma unroll
+        for (int i = 0; i < NU; ++i) u[i] = ws[L.w + iu(k, i)];
+        if (blocked(k)) u[0] = x[NX - 1];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) lamn[i] = 0.0;
+        Model::der(P, x, u, pg(), ps(k), lamn, df, false, xn, A, B, &q, gq, W);
+        if (blocked(k)) fold_blocked(A, B, gq, nullptr);
+        fsum += q;
+#pragma unroll
+        for (int i = 0; i < NX * NX; ++i) ws[L.ab + k * NAB + i] = A[i];
+#pragma unroll
+        for (int i = 0; i < NX * NU; ++i) ws[L.ab + k * NAB + NX * NX + i] = B[i];
+        // stash dq/dz in the Hessian slot until the costates are known
+#pragma unroll
+        for (int i = 0; i < NZ; ++i) ws[L.hw + k * NW + i] = gq[i];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) { x[i] = xn[i]; ws[L.xs + (k + 1) * NX + i] = xn[i]; }
+      }
+      f_curr = df * fsum;
+      // backward costate (adjoint) sweep: mu_N = 0, mu_k = df q_x + A_k' mu_{k+1};
+      // reduced gradient dJ/du_k = df q_u + B_k' mu_{k+1}
+#pragma unroll
+      for (int i = 0; i < NX; ++i) { ws[L.lam + N * NX + i] = 0.0; lamn[i] = 0.0; }
+      for (int k = N - 1; k >= 0; --k) {
+        double mk[NX];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+          double v = df * ws[L.hw + k * NW + NX + i];
+#pragma unroll
+          for (int j = 0; j < NX; ++j) v += ws[L.ab + k * NAB + NX * NX + j * NU + i] * lamn[j];
+          ws[L.grad + iu(k, i)] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+          double v = df * ws[L.hw + k * NW + i];
+#pragma unroll
+          for (int j = 0; j < NX; ++j) v += ws[L.ab + k * NAB + j * NX + i] * lamn[j];
+          mk[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) { lamn[i] = mk[i]; ws[L.lam + k * NX + i] = mk[i]; }
+      }
+      if (want_hess) {
+        for (int k = 0; k < N; ++k) {
+#pragma unroll
+          for (int i = 0; i < NX; ++i) { x[i] = ws[L.xs + k * NX + i]; lamn[i] = ws[L.lam + (k + 1) * NX + i]; }
+#pragma unroll
+          for (int i = 0; i < NU; ++i) u[i] = ws[L.w + iu(k, i)];
+          if (blocked(k)) u[0] = x[NX - 1];
+          Model::der(P, x, u, pg(), ps(k), lamn, df, true, xn, A, B, &q, gq, W);
+          if (blocked(k)) fold_blocked(A, B, gq, W);
+#pragma unroll
+          for (int i = 0; i < NW; ++i) ws[L.hw + k * NW + i] = W[i];
+        }
+      }
+    }
+    f_curr = g.sum(g.lane == 0 ? f_curr : 0.0);
+    g.sync();
+  }
+
+  // ---- objective / constraint violation / barrier at  w + alpha * (vector at doff) -------------
+  // returns scaled f; theta = ||c||_1; barrier log terms; optionally stores the residuals in ct
+  MPCV_DN void eval_trial(double alpha, int doff, bool store_ct, double* f_out, double* theta_out,
+                         double* phi_out) const {
+    double fpart = 0.0, thpart = 0.0, logpart = 0.0;
+    bool bad = false;
+    if (SINGLE) {
+      if (g.lane == 0) {
+        double x[NX], u[NU], xn[NX], q;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) x[i] = ws[L.par + i];
+        for (int k = 0; k < N; ++k) {
+#pragma unroll
+          for (int i = 0; i < NU; ++i) u[i] = ws[L.w + iu(k, i)] + alpha * ws[doff + iu(k, i)];
+          if (blocked(k)) u[0] = x[NX - 1];
+          Model::val(P, x, u, pg(), ps(k), xn, &q);
+          fpart += q;
+#pragma unroll
+          for (int i = 0; i < NX; ++i) x[i] = xn[i];
+        }
+      }
+    } else {
+      for (int k = g.lane; k < N; k += LANES) {
+        double x[NX], u[NU], xn[NX], q;
+        load_xu(k, L.w, alpha, doff, x, u);
+        Model::val(P, x, u, pg(), ps(k), xn, &q);
+        fpart += q;
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+          const double r = xn[i] - (ws[L.w + ix(k + 1, i)] + alpha * ws[doff + ix(k + 1, i)]);
+          thpart += fabs(r);
+          if (store_ct) ws[L.ct + (k + 1) * NX + i] = r;
+        }
+      }
+      if (g.lane == 0) {
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+          const double r = ws[L.par + i] - (ws[L.w + ix(0, i)] + alpha * ws[doff + ix(0, i)]);
+          thpart += fabs(r);
+          if (store_ct) ws[L.ct + i] = r;
+        }
+      }
+    }
+    for (int i = g.lane; i < L.n; i += LANES) {
+      const Bnd b = bnd(i);
+      if (b.hasl || b.hasu) {
+        const double v = ws[L.w + i] + alpha * ws[doff + i];
+        if (b.hasl) { const double s = v - b.lo; if (!(s > 0.0)) bad = true; logpart += log(s); }
+        if (b.hasu) { const double s = b.hi - v; if (!(s > 0.0)) bad = true; logpart += log(s); }
+      }
+    }
+    const double f = df * g.sum(fpart);
+    const double th = g.sum(thpart);
+    double lg = g.sum(logpart);
+    const bool anybad = g.max(bad ? 1.0 : 0.0) > 0.0;
+    *f_out = f;
+    *theta_out = th;
+    *phi_out = anybad ? INFINITY : f - mu * lg;
+    if (store_ct) g.sync();
+  }
+
+  // ---- error measures (scaled as in IPOPT's E_mu) ------------------------------------------------
+  struct Err { double dual, prim, cmin, cmax, sd, sc; bool any_bound; };
+  MPCV_DN Err errors() const {
+    double dual = 0.0, prim = 0.0, cmin = INFINITY, cmax = -INFINITY, zsum = 0.0, lsum = 0.0, nz = 0.0;
+    // dual infeasibility  grad + J' lam - zl + zu, stage-parallel
+    if (SINGLE) {
+      for (int i = g.lane; i < L.n; i += LANES) {
+        const Bnd b = bnd(i);
+        if (b.fixed) continue;
+        dual = fmax(dual, fabs(ws[L.grad + i] - ws[L.zl + i] + ws[L.zu + i]));
+      }
+    } else {
+      for (int k = g.lane; k <= N; k += LANES) {
+        double lk[NX], ln[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) { lk[i] = ws[L.lam + k * NX + i]; ln[i] = (k < N) ? ws[L.lam + (k + 1) * NX + i] : 0.0; }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+          const int v = ix(k, i);
+          double d = ws[L.grad + v] - lk[i] - ws[L.zl + v] + ws[L.zu + v];
+          if (k < N) {
+#pragma unroll
+            for (int j = 0; j < NX; ++j) d += ws[L.ab + k * NAB + j * NX + i] * ln[j];
+          }
+          dual = fmax(dual, fabs(d));
+        }
+        if (k < N) {
+#pragma unroll
+          for (int i = 0; i < NU; ++i) {
+            const int v = iu(k, i);
+            if (bnd(v).fixed) continue;
+            double d = ws[L.grad + v] - ws[L.zl + v] + ws[L.zu + v];
+#pragma unroll
+            for (int j = 0; j < NX; ++j) d += ws[L.ab + k * NAB + NX * NX + j * NU + i] * ln[j];
+            dual = fmax(dual, fabs(d));
+          }
+        }
+      }
+      for (int i = g.lane; i < L.m; i += LANES) {
+        prim = fmax(prim, fabs(ws[L.c + i]));
+        lsum += fabs(ws[L.lam + i]);
+      }
+    }
+    for (int i = g.lane; i < L.n; i += LANES) {
+      const Bnd b = bnd(i);
+      if (b.hasl) {
+        const double z = ws[L.zl + i], c = (ws[L.w + i] - b.lo) * z;
+        cmin = fmin(cmin, c); cmax = fmax(cmax, c); zsum += fabs(z); nz += 1.0;
+      }
+      if (b.hasu) {
+        const double z = ws[L.zu + i], c = (b.hi - ws[L.w + i]) * z;
+        cmin = fmin(cmin, c); cmax = fmax(cmax, c); zsum += fabs(z); nz += 1.0;
+      }
+    }
+    Err e;
+    dual = g.max(dual); prim = g.max(prim); e.cmin = g.min(cmin); e.cmax = g.max(cmax);
+    zsum = g.sum(zsum); lsum = g.sum(lsum); nz = g.sum(nz);
+    const double s_max = 100.0;
+    e.any_bound = nz > 0.0;
+    e.sd = (L.m + nz > 0.0) ? fmax(s_max, (lsum + zsum) / (L.m + nz)) / s_max : 1.0;
+    e.sc = e.any_bound ? fmax(s_max, zsum / nz) / s_max : 1.0;
+    e.dual = dual / e.sd;
+    e.prim = prim;
+    return e;
+  }
+  MPCV_D static double compl_err(const Err& e, double mu_t) {
+    if (!e.any_bound) return 0.0;
+    return fmax(fabs(e.cmax - mu_t), fabs(e.cmin - mu_t)) / e.sc;
+  }
+  MPCV_D static double Emu(const Err& e, double mu_t) { return fmax(e.dual, fmax(e.prim, compl_err(e, mu_t))); }
+
+  // ---- Sigma and barrier gradient of variable i -----------------------------------------------------
+  MPCV_D void sigma_r(int i, double* sg, double* r) const {
+    const Bnd b = bnd(i);
+    double s = 0.0, ri = ws[L.grad + i];
+    if (b.hasl) { const double sl = ws[L.w + i] - b.lo; s += ws[L.zl + i] / sl; ri -= mu / sl; }
+    if (b.hasu) { const double su = b.hi - ws[L.w + i]; s += ws[L.zu + i] / su; ri += mu / su; }
+    *sg = s; *r = ri;
+  }
+
+  // ---- Riccati factorisation (multiple shooting) ------------------------------------------------------
+  // identity=true replaces the Lagrangian Hessian by I and drops Sigma (least-squares multipliers).
+  // Stores per stage: K (NU x NX), chol(F) packed, P_k packed; returns false on wrong inertia.
+  MPCV_DN bool riccati_factor(double dw, bool identity) {
+    int ok = 1;
+    if (g.lane == 0) {
+      double Pm[NX * NX];   // P_{k+1}, full symmetric
+#pragma unroll
+      for (int i = 0; i < NX * NX; ++i) Pm[i] = 0.0;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        double sg = 0.0, r;
+        if (!identity) sigma_r(ix(N, i), &sg, &r);
+        Pm[i * NX + i] = (identity ? 1.0 : 0.0) + sg + dw;
+      }
+      store_P(N, Pm);
+      for (int k = N - 1; k >= 0 && ok; --k) {
+        double A[NX * NX], B[NX * NU], W[NW];
+#pragma unroll
+        for (int i = 0; i < NX * NX; ++i) A[i] = ws[L.ab + k * NAB + i];
+#pragma unroll
+        for (int i = 0; i < NX * NU; ++i) B[i] = ws[L.ab + k * NAB + NX * NX + i];
+        if (identity) {
+#pragma unroll
+          for (int i = 0; i < NW; ++i) W[i] = 0.0;
+#pragma unroll
+          for (int i = 0; i < NZ; ++i) W[tri(i, i)] = 1.0;
+        } else {
+#pragma unroll
+          for (int i = 0; i < NW; ++i) W[i] = ws[L.hw + k * NW + i];
+#pragma unroll
+          for (int i = 0; i < NZ; ++i) {
+            double sg, r;
+            sigma_r(k * NZ + i, &sg, &r);
+            W[tri(i, i)] += sg + dw;
+          }
+        }
+        // PA = P A, PB = P B
+        double PA[NX * NX], PB[NX * NU];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+#pragma unroll
+          for (int j = 0; j < NX; ++j) {
+            double v = 0.0;
+#pragma unroll
+            for (int l = 0; l < NX; ++l) v += Pm[i * NX + l] * A[l * NX + j];
+            PA[i * NX + j] = v;
+          }
+#pragma unroll
+          for (int j = 0; j < NU; ++j) {
+            double v = 0.0;
+#pragma unroll
+            for (int l = 0; l < NX; ++l) v += Pm[i * NX + l] * B[l * NU + j];
+            PB[i * NU + j] = v;
+          }
+        }
+        // F = Ruu + B'PB (lower), G = Sux + B'PA
+        double F[NU * NU], G[NU * NX];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+#pragma unroll
+          for (int j = 0; j <= i; ++j) {
+            double v = W[tri(NX + i, NX + j)];
+#pragma unroll
+            for (int l = 0; l < NX; ++l) v += B[l * NU + i] * PB[l * NU + j];
+            F[i * NU + j] = v;
+          }
+#pragma unroll
+          for (int j = 0; j < NX; ++j) {
+            double v = W[tri(NX + i, j)];
+#pragma unroll
+            for (int l = 0; l < NX; ++l) v += B[l * NU + i] * PA[l * NX + j];
+            G[i * NX + j] = v;
+          }
+        }
+        // fixed controls (blocked / lb == ub): unit pivot, no coupling
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+          if (bnd(iu(k, i)).fixed) {
+#pragma unroll
+            for (int j = 0; j < NU; ++j) { if (j <= i) F[i * NU + j] = 0.0; else F[j * NU + i] = 0.0; }
+            F[i * NU + i] = 1.0;
+#pragma unroll
+            for (int j = 0; j < NX; ++j) G[i * NX + j] = 0.0;
+          }
+        }
+        // Cholesky of F in place (lower)
+#pragma unroll
+        for (int j = 0; j < NU; ++j) {
+          double dj = F[j * NU + j];
+#pragma unroll
+          for (int l = 0; l < j; ++l) dj -= F[j * NU + l] * F[j * NU + l];
+          if (!(dj > 0.0) || !(dj < INFINITY)) { ok = 0; dj = 1.0; }
+          dj = sqrt(dj);
+          F[j * NU + j] = dj;
+#pragma unroll
+          for (int i = j + 1; i < NU; ++i) {
+            double v = F[i * NU + j];
+#pragma unroll
+            for (int l = 0; l < j; ++l) v -= F[i * NU + l] * F[j * NU + l];
+            F[i * NU + j] = v / dj;
+          }
+        }
+        // K = -F^{-1} G  (column by column)
+        double K[NU * NX];
+#pragma unroll
+        for (int c = 0; c < NX; ++c) {
+          double t[NU];
+#pragma unroll
+          for (int i = 0; i < NU; ++i) {
+            double v = -G[i * NX + c];
+#pragma unroll
+            for (int l = 0; l < i; ++l) v -= F[i * NU + l] * t[l];
+            t[i] = v / F[i * NU + i];
+          }
+#pragma unroll
+          for (int i = NU - 1; i >= 0; --i) {
+            double v = t[i];
+#pragma unroll
+            for (int l = i + 1; l < NU; ++l) v -= F[l * NU + i] * t[l];
+            t[i] = v / F[i * NU + i];
+          }
+#pragma unroll
+          for (int i = 0; i < NU; ++i) K[i * NX + c] = t[i];
+        }
+        // P_k = Qxx + A'PA + G'K  (symmetric)
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+#pragma unroll
+          for (int j = 0; j <= i; ++j) {
+            double v = W[tri(i, j)];
+#pragma unroll
+            for (int l = 0; l < NX; ++l) v += A[l * NX + i] * PA[l * NX + j];
+#pragma unroll
+            for (int l = 0; l < NU; ++l) v += G[l * NX + i] * K[l * NX + j];
+            Pm[i * NX + j] = v;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+#pragma unroll
+          for (int j = i + 1; j < NX; ++j) Pm[i * NX + j] = Pm[j * NX + i];
+        }
+        store_P(k, Pm);
+        const int ro = L.ric + k * NRIC;
+#pragma unroll
+        for (int i = 0; i < NU * NX; ++i) ws[ro + i] = K[i];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+#pragma unroll
+          for (int j = 0; j <= i; ++j) ws[ro + NU * NX + NU + tri(i, j)] = F[i * NU + j];
+        }
+      }
+    }
+    ok = g.bcast(ok);
+    g.sync();
+    return ok != 0;
+  }
+  MPCV_D void store_P(int k, const double* Pm) const {
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+#pragma unroll
+      for (int j = 0; j <= i; ++j) ws[L.pp + k * NPP + tri(i, j)] = Pm[i * NX + j];
+    }
+  }
+  MPCV_D void load_P(int k, double* Pm) const {
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+#pragma unroll
+      for (int j = 0; j <= i; ++j) { const double v = ws[L.pp + k * NPP + tri(i, j)]; Pm[i * NX + j] = v; Pm[j * NX + i] = v; }
+    }
+  }
+
+  // ---- Riccati solve: vector recursions with the stored factors ------------------------------------
+  // rhs: r = barrier gradient (rmode 0) or grad - zl + zu (rmode 1, least squares);
+  // residuals from offset coff (L.c, L.ct) or zero (coff < 0).  Writes d and lam+ (L.lamp).
+  MPCV_DN void riccati_solve(int rmode, int coff) const {
+    if (g.lane == 0) {
+      double pv[NX];   // p_{k+1}
+      auto rvar = [&](int v) {
+        if (rmode == 1) return ws[L.grad + v] - ws[L.zl + v] + ws[L.zu + v];
+        double sg, r; sigma_r(v, &sg, &r); return r;
+      };
+#pragma unroll
+      for (int i = 0; i < NX; ++i) { pv[i] = rvar(ix(N, i)); ws[L.pp + N * NPP + NPX + i] = pv[i]; }
+      for (int k = N - 1; k >= 0; --k) {
+        double Pm[NX * NX], Pd[NX], gk[NU], t[NU];
+        load_P(k + 1, Pm);
+        // Pd = P_{k+1} c_{k+1} + p_{k+1}
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+          double v = pv[i];
+          if (coff >= 0) {
+#pragma unroll
+            for (int j = 0; j < NX; ++j) v += Pm[i * NX + j] * ws[coff + (k + 1) * NX + j];
+          }
+          Pd[i] = v;
+        }
+        const int ao = L.ab + k * NAB, ro = L.ric + k * NRIC;
+        // g = r_u + B' Pd ; kff = -F^{-1} g
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+          double v = rvar(iu(k, i));
+#pragma unroll
+          for (int j = 0; j < NX; ++j) v += ws[ao + NX * NX + j * NU + i] * Pd[j];
+          if (bnd(iu(k, i)).fixed) v = 0.0;
+          gk[i] = v;
+        }
+        double F[NU * NU];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+#pragma unroll
+          for (int j = 0; j <= i; ++j) F[i * NU + j] = ws[ro + NU * NX + NU + tri(i, j)];
+        }
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+          double v = -gk[i];
+#pragma unroll
+          for (int l = 0; l < i; ++l) v -= F[i * NU + l] * t[l];
+          t[i] = v / F[i * NU + i];
+        }
+#pragma unroll
+        for (int i = NU - 1; i >= 0; --i) {
+          double v = t[i];
+#pragma unroll
+          for (int l = i + 1; l < NU; ++l) v -= F[l * NU + i] * t[l];
+          t[i] = v / F[i * NU + i];
+        }
+#pragma unroll
+        for (int i = 0; i < NU; ++i) ws[ro + NU * NX + i] = t[i];
+        // p_k = r_x + A' Pd + K' g
+        double pk[NX];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+          double v = rvar(ix(k, i));
+#pragma unroll
+          for (int j = 0; j < NX; ++j) v += ws[ao + j * NX + i] * Pd[j];
+#pragma unroll
+          for (int j = 0; j < NU; ++j) v += ws[ro + j * NX + i] * gk[j];
+          pk[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) { pv[i] = pk[i]; ws[L.pp + k * NPP + NPX + i] = pk[i]; }
+      }
+      // forward sweep: dx_0 = c_0, du = K dx + kff, dx+ = A dx + B du + c+, lam+_k = P_k dx_k + p_k
+      double dx[NX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) dx[i] = (coff >= 0) ? ws[coff + i] : 0.0;
+      for (int k = 0; k <= N; ++k) {
+        double Pm[NX * NX];
+        load_P(k, Pm);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+          double v = ws[L.pp + k * NPP + NPX + i];
+#pragma unroll
+          for (int j = 0; j < NX; ++j) v += Pm[i * NX + j] * dx[j];
+          ws[L.lamp + k * NX + i] = v;
+          ws[L.d + ix(k, i)] = dx[i];
+        }
+        if (k == N) break;
+        const int ao = L.ab + k * NAB, ro = L.ric + k * NRIC;
+        double du[NU], dn[NX];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+          double v = ws[ro + NU * NX + i];
+#pragma unroll
+          for (int j = 0; j < NX; ++j) v += ws[ro + i * NX + j] * dx[j];
+          du[i] = v;
+          ws[L.d + iu(k, i)] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+          double v = (coff >= 0) ? ws[coff + (k + 1) * NX + i] : 0.0;
+#pragma unroll
+          for (int j = 0; j < NX; ++j) v += ws[ao + i * NX + j] * dx[j];
+#pragma unroll
+          for (int j = 0; j < NU; ++j) v += ws[ao + NX * NX + i * NU + j] * du[j];
+          dn[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) dx[i] = dn[i];
+      }
+    }
+    g.sync();
+  }
+
+  // ---- single shooting: condensed Hessian, dense Cholesky ---------------------------------------------
+  // H = sum_k S_k' W_k S_k,  S_k = d(x_k,u_k)/dU,  W_k with the costates as multipliers.
+  MPCV_DN bool condensed_factor(double dw) {
+    int ok = 1;
+    const int nU = NU * N;
+    if (g.lane == 0) {
+      const int H = L.hred, Gm = L.gam, Tm = L.tmp;
+      for (int i = 0; i < nU * (nU + 1) / 2; ++i) ws[H + i] = 0.0;
+      for (int i = 0; i < NX * nU; ++i) ws[Gm + i] = 0.0;
+      for (int k = 0; k < N; ++k) {
+        const int ncol = NU * (k + 1);
+        double W[NW];
+#pragma unroll
+        for (int i = 0; i < NW; ++i) W[i] = ws[L.hw + k * NW + i];
+        auto Wf = [&](int a, int b) { return a >= b ? W[tri(a, b)] : W[tri(b, a)]; };
+        // T = W S  (NZ x ncol); S rows 0..NX-1 = Gamma_k, rows NX.. = unit columns of stage k
+        for (int c = 0; c < ncol; ++c) {
+#pragma unroll
+          for (int a = 0; a < NZ; ++a) {
+            double v = 0.0;
+#pragma unroll
+            for (int b = 0; b < NX; ++b) v += Wf(a, b) * ws[Gm + b * nU + c];
+            if (c >= NU * k) v += Wf(a, NX + c - NU * k);
+            ws[Tm + a * nU + c] = v;
+          }
+        }
+        for (int r = 0; r < ncol; ++r) {
+          for (int c = 0; c <= r; ++c) {
+            double v = 0.0;
+#pragma unroll
+            for (int a = 0; a < NX; ++a) v += ws[Gm + a * nU + r] * ws[Tm + a * nU + c];
+            if (r >= NU * k) v += ws[Tm + (NX + r - NU * k) * nU + c];
+            ws[H + tri(r, c)] += v;
+          }
+        }
+        // Gamma_{k+1} = A Gamma_k + B E_k
+        const int ao = L.ab + k * NAB;
+        for (int c = 0; c < ncol; ++c) {
+          double col[NX], out[NX];
+#pragma unroll
+          for (int b = 0; b < NX; ++b) col[b] = ws[Gm + b * nU + c];
+#pragma unroll
+          for (int a = 0; a < NX; ++a) {
+            double v = 0.0;
+#pragma unroll
+            for (int b = 0; b < NX; ++b) v += ws[ao + a * NX + b] * col[b];
+            if (c >= NU * k) v += ws[ao + NX * NX + a * NU + (c - NU * k)];
+            out[a] = v;
+          }
+#pragma unroll
+          for (int a = 0; a < NX; ++a) ws[Gm + a * nU + c] = out[a];
+        }
+      }
+      for (int i = 0; i < nU; ++i) {
+        const Bnd b = bnd(i);
+        if (b.fixed) {
+          for (int j = 0; j < nU; ++j) ws[H + (j <= i ? tri(i, j) : tri(j, i))] = 0.0;
+          ws[H + tri(i, i)] = 1.0;
+        } else {
+          double sg, r;
+          sigma_r(i, &sg, &r);
+          ws[H + tri(i, i)] += sg + dw;
+        }
+      }
+      // packed Cholesky
+      for (int j = 0; j < nU && ok; ++j) {
+        double dj = ws[H + tri(j, j)];
+        for (int l = 0; l < j; ++l) { const double t = ws[H + tri(j, l)]; dj -= t * t; }
+        if (!(dj > 0.0) || !(dj < INFINITY)) { ok = 0; break; }
+        dj = sqrt(dj);
+        ws[H + tri(j, j)] = dj;
+        for (int i = j + 1; i < nU; ++i) {
+          double v = ws[H + tri(i, j)];
+          for (int l = 0; l < j; ++l) v -= ws[H + tri(i, l)] * ws[H + tri(j, l)];
+          ws[H + tri(i, j)] = v / dj;
+        }
+      }
+    }
+    ok = g.bcast(ok);
+    g.sync();
+    return ok != 0;
+  }
+  MPCV_DN void condensed_solve() const {
+    const int nU = NU * N;
+    if (g.lane == 0) {
+      const int H = L.hred;
+      for (int i = 0; i < nU; ++i) {
+        double sg, r;
+        sigma_r(i, &sg, &r);
+        double v = bnd(i).fixed ? 0.0 : -r;
+        for (int l = 0; l < i; ++l) v -= ws[H + tri(i, l)] * ws[L.d + l];
+        ws[L.d + i] = v / ws[H + tri(i, i)];
+      }
+      for (int i = nU - 1; i >= 0; --i) {
+        double v = ws[L.d + i];
+        for (int l = i + 1; l < nU; ++l) v -= ws[H + tri(l, i)] * ws[L.d + l];
+        ws[L.d + i] = v / ws[H + tri(i, i)];
+      }
+    }
+    g.sync();
+  }
+
+  // ---- step-length helpers ----------------------------------------------------------------------------
+  MPCV_D double dz_l(int i, const Bnd& b) const {
+    const double sl = ws[L.w + i] - b.lo;
+    return mu / sl - ws[L.zl + i] - ws[L.zl + i] / sl * ws[L.d + i];
+  }
+  MPCV_D double dz_u(int i, const Bnd& b) const {
+    const double su = b.hi - ws[L.w + i];
+    return mu / su - ws[L.zu + i] + ws[L.zu + i] / su * ws[L.d + i];
+  }
+  MPCV_D double ftb_primal() const {
+    double a = 1.0;
+    for (int i = g.lane; i < L.n; i += LANES) {
+      const Bnd b = bnd(i);
+      const double di = ws[L.d + i];
+      if (b.hasl && di < 0.0) a = fmin(a, -tau * (ws[L.w + i] - b.lo) / di);
+      if (b.hasu && di > 0.0) a = fmin(a, tau * (b.hi - ws[L.w + i]) / di);
+    }
+    return g.min(a);
+  }
+  MPCV_D double ftb_dual() const {
+    double a = 1.0;
+    for (int i = g.lane; i < L.n; i += LANES) {
+      const Bnd b = bnd(i);
+      if (b.hasl) { const double dz = dz_l(i, b); if (dz < 0.0) a = fmin(a, -tau * ws[L.zl + i] / dz); }
+      if (b.hasu) { const double dz = dz_u(i, b); if (dz < 0.0) a = fmin(a, -tau * ws[L.zu + i] / dz); }
+    }
+    return g.min(a);
+  }
+
+  // mirror blocked controls from their predecessor so outputs read like MPCTools' u trajectory
+  MPCV_D void sync_blocked() const {
+    if (!(Model::HAS_UPREV && P.ntu > 0)) return;
+    if (g.lane == 0)
+      for (int k = (P.ntu > 1 ? P.ntu : 1); k < N; ++k) ws[L.w + iu(k, 0)] = ws[L.w + iu(k - 1, 0)];
+    g.sync();
+  }
+
+  // ---- the solve ------------------------------------------------------------------------------------------
+  // On entry ws[L.w..] holds the starting point and ws[L.par..] the parameters.
+  MPCV_DN SolveInfo solve() {
+    SolveInfo info;
+    const double eps = 2.220446049250313e-16;
+    // push the starting point into the interior (bound_push / bound_frac); fixed variables take their value
+    for (int i = g.lane; i < L.n; i += LANES) {
+      const Bnd b = bnd(i);
+      double v = ws[L.w + i];
+      if (b.fixed && !var_is_blocked_u(i)) v = lbx[i];
+      if (b.hasl && b.hasu) {
+        const double pl = fmin(P.bound_push * fmax(1.0, fabs(b.lo)), P.bound_frac * (b.hi - b.lo));
+        const double pu = fmin(P.bound_push * fmax(1.0, fabs(b.hi)), P.bound_frac * (b.hi - b.lo));
+        v = fmin(fmax(v, b.lo + pl), b.hi - pu);
+      } else if (b.hasl) {
+        v = fmax(v, b.lo + P.bound_push * fmax(1.0, fabs(b.lo)));
+      } else if (b.hasu) {
+        v = fmin(v, b.hi - P.bound_push * fmax(1.0, fabs(b.hi)));
+      }
+      ws[L.w + i] = v;
+      ws[L.zl + i] = b.hasl ? 1.0 : 0.0;
+      ws[L.zu + i] = b.hasu ? 1.0 : 0.0;
+    }
+    for (int i = g.lane; i < NX * (N + 1); i += LANES) ws[L.lam + i] = 0.0;
+    g.sync();
+    sync_blocked();
+    // gradient-based objective scaling at the starting point (nlp_scaling_max_gradient)
+    df = 1.0;
+    eval_derivatives(false);
+    {
+      double gmax = 0.0;
+      for (int i = g.lane; i < L.n; i += LANES)
+        if (!bnd(i).fixed) gmax = fmax(gmax, fabs(ws[L.grad + i]));
+      gmax = g.max(gmax);
+      if (gmax > P.scal_max_grad) {
+        df = fmax(P.scal_max_grad / gmax, 1e-8);
+        eval_derivatives(false);
+      }
+    }
+    mu = P.mu_init;
+    tau = fmax(0.99, 1.0 - mu);
+    nfil = 0;
+    // least-squares multipliers  [I J'; J 0][.; lam] = -[grad f - zl + zu; 0]
+    if (!SINGLE) {
+      if (riccati_factor(0.0, true)) {
+        riccati_solve(1, -1);
+        double lmax = 0.0;
+        for (int i = g.lane; i < L.m; i += LANES) lmax = fmax(lmax, fabs(ws[L.lamp + i]));
+        lmax = g.max(lmax);
+        if (lmax <= 1e3) {
+          for (int i = g.lane; i < L.m; i += LANES) ws[L.lam + i] = ws[L.lamp + i];
+        }
+        g.sync();
+      }
+    }
+    eval_derivatives(true);
+
+    double theta_max = -1.0, theta_min = -1.0, delta_w_last = 0.0;
+    int iter = 0;
+    info.status = MPCV_MAXIMUM_ITERATIONS_EXCEEDED;
+    for (;; ++iter) {
+      // --- convergence test ---
+      const Err e = errors();
+      const double E0 = Emu(e, 0.0);
+      {
+        const double dual_u = e.dual * e.sd / df, compl_u = compl_err(e, 0.0) * e.sc / df;
+        if (E0 <= P.tol && dual_u <= P.dual_inf_tol && e.prim <= P.constr_viol_tol && compl_u <= P.compl_inf_tol) {
+          info.status = MPCV_SOLVE_SUCCEEDED;
+          break;
+        }
+      }
+      if (iter >= P.max_iter) { info.status = MPCV_MAXIMUM_ITERATIONS_EXCEEDED; break; }
+      if (!(E0 < INFINITY)) { info.status = MPCV_INVALID_NUMBER_DETECTED; break; }
+      // --- monotone barrier update ---
+      {
+        bool done = false;
+        while (!done && Emu(e, mu) <= 10.0 * mu) {
+          double new_mu = fmin(0.2 * mu, pow(mu, 1.5));
+          new_mu = fmax(new_mu, fmin(P.tol, P.compl_inf_tol * df) / 11.0);
+          const bool changed = new_mu != mu;
+          mu = new_mu;
+          tau = fmax(0.99, 1.0 - mu);
+          if (!changed) done = true; else nfil = 0;
+        }
+      }
+      // --- search direction with inertia correction ---
+      double dw = 0.0;
+      bool ok = SINGLE ? condensed_factor(0.0) : riccati_factor(0.0, false);
+      while (!ok) {
+        if (dw == 0.0) dw = (delta_w_last == 0.0) ? 1e-4 : fmax(1e-20, delta_w_last / 3.0);
+        else dw *= (delta_w_last == 0.0 || 1e5 * delta_w_last < dw) ? 100.0 : 8.0;
+        if (dw > 1e20) break;
+        ok = SINGLE ? condensed_factor(dw) : riccati_factor(dw, false);
+      }
+      if (!ok) { info.status = MPCV_ERROR_IN_STEP_COMPUTATION; break; }
+      if (dw > 0.0) delta_w_last = dw;
+      if (SINGLE) condensed_solve(); else riccati_solve(0, L.c);
+      double alpha_max = ftb_primal();
+      // --- filter line search ---
+      double theta = 0.0, gBD = 0.0, lg = 0.0;
+      for (int i = g.lane; i < L.m; i += LANES) theta += fabs(ws[L.c + i]);
+      for (int i = g.lane; i < L.n; i += LANES) {
+        double sg, r;
+        sigma_r(i, &sg, &r);
+        if (!bnd(i).fixed) gBD += r * ws[L.d + i];
+        const Bnd b = bnd(i);
+        if (b.hasl) lg += log(ws[L.w + i] - b.lo);
+        if (b.hasu) lg += log(b.hi - ws[L.w + i]);
+      }
+      theta = g.sum(theta); gBD = g.sum(gBD); lg = g.sum(lg);
+      const double phi = f_curr - mu * lg;
+      if (theta_max < 0.0) { theta_max = 1e4 * fmax(1.0, theta); theta_min = 1e-4 * fmax(1.0, theta); }
+      double alpha_min = 1e-5;
+      if (gBD < 0.0) {
+        alpha_min = fmin(1e-5, 1e-8 * theta / (-gBD));
+        if (theta <= theta_min) alpha_min = fmin(alpha_min, pow(theta, 1.1) / pow(-gBD, 2.3));
+      }
+      alpha_min *= 0.05;
+      auto is_ftype = [&](double a) {
+        if (theta == 0.0 && gBD > 0.0 && gBD < 100.0 * eps) return true;
+        return gBD < 0.0 && a * pow(-gBD, 2.3) > pow(theta, 1.1);
+      };
+      auto armijo = [&](double a, double phi_t) { return compare_le(phi_t - phi, 1e-8 * a * gBD, phi); };
+      auto acceptable = [&](double a, double phi_t, double theta_t) {
+        if (!(phi_t < INFINITY) || !(theta_t < INFINITY) || phi_t != phi_t) return false;
+        if (theta_max > 0.0 && theta_t > theta_max) return false;
+        bool acc;
+        if (a > 0.0 && is_ftype(a) && theta <= theta_min) acc = armijo(a, phi_t);
+        else {
+          if (phi_t > phi) {
+            double basval = 1.0;
+            if (fabs(phi) > 10.0) basval = log10(fabs(phi));
+            if (log10(phi_t - phi) > 5.0 + basval) return false;
+          }
+          acc = compare_le(theta_t, (1.0 - 1e-5) * theta, theta) || compare_le(phi_t - phi, -1e-8 * theta, phi);
+        }
+        if (!acc) return false;
+        for (int q = 0; q < nfil; ++q)
+          if (!(compare_le(phi_t, fil_phi[q], fil_phi[q]) || compare_le(theta_t, fil_th[q], fil_th[q]))) return false;
+        return true;
+      };
+      double alpha = alpha_max, alpha_test = alpha_max, phi_acc = 0.0;
+      bool accepted = false, soc_step = false;
+      int nsteps = 0;
+      while (alpha > alpha_min || nsteps == 0) {
+        double f_t, theta_t, phi_t;
+        eval_trial(alpha, L.d, !SINGLE && nsteps == 0 && P.max_soc > 0, &f_t, &theta_t, &phi_t);
+        alpha_test = alpha;
+        if (acceptable(alpha, phi_t, theta_t)) { accepted = true; phi_acc = phi_t; break; }
+        // second-order correction on the first rejected trial
+        if (!SINGLE && nsteps == 0 && P.max_soc > 0 && theta_t >= theta) {
+          // keep the plain step in lamp?  no: SOC overwrites d and lamp; save the plain step in grad-free slots
+          // c_soc accumulates in ct: c_soc = ct + alpha_soc * c_soc (c_soc starts as c)
+          double theta_soc_old = 0.0, theta_tr = theta_t, alpha_soc = alpha;
+          int count = 0;
+          bool acc_soc = false;
+          // save the plain direction so that a failed SOC can fall back to backtracking
+          save_step();
+          // csoc lives in ct: first  csoc = ct + alpha*c
+          for (int i = g.lane; i < L.m; i += LANES) ws[L.ct + i] = ws[L.ct + i] + alpha_soc * ws[L.c + i];
+          g.sync();
+          while (count < P.max_soc && !acc_soc && (count == 0 || theta_tr <= 0.99 * theta_soc_old)) {
+            theta_soc_old = theta_tr;
+            riccati_solve(0, L.ct);
+            alpha_soc = ftb_primal();
+            double f_s, theta_s, phi_s;
+            // trial residuals needed for a possible next correction: store into lamp-sized scratch (c slot is live) -> use tmp in pp? reuse ct after combining
+            eval_trial_soc(alpha_soc, &f_s, &theta_s, &phi_s);
+            if (acceptable(alpha, phi_s, theta_s)) { acc_soc = true; alpha = alpha_soc; phi_acc = phi_s; }
+            else { ++count; theta_tr = theta_s; }
+          }
+          if (acc_soc) { accepted = true; soc_step = true; break; }
+          restore_step();
+        }
+        alpha *= 0.5;
+        ++nsteps;
+      }
+      (void)soc_step;
+      if (!accepted) { info.status = MPCV_RESTORATION_FAILED; break; }
+      if (!is_ftype(alpha_test) || !armijo(alpha_test, phi_acc)) {
+        if (nfil < FILTER_MAX) {
+          fil_phi[nfil] = phi - 1e-8 * theta; fil_th[nfil] = (1.0 - 1e-5) * theta; ++nfil;
+        } else {
+          // filter full: overwrite the entry dominated most weakly (oldest)
+          for (int q = 1; q < FILTER_MAX; ++q) { fil_phi[q - 1] = fil_phi[q]; fil_th[q - 1] = fil_th[q]; }
+          fil_phi[FILTER_MAX - 1] = phi - 1e-8 * theta; fil_th[FILTER_MAX - 1] = (1.0 - 1e-5) * theta;
+        }
+      }
+      const double alpha_dual = ftb_dual();
+      // --- accept the trial point ---
+      for (int i = g.lane; i < L.n; i += LANES) {
+        const Bnd b = bnd(i);
+        const double dzl = b.hasl ? dz_l(i, b) : 0.0, dzu = b.hasu ? dz_u(i, b) : 0.0;
+        const double wi = ws[L.w + i] + alpha * ws[L.d + i];
+        ws[L.w + i] = wi;
+        if (b.hasl) {
+          const double sl = wi - b.lo;
+          double z = ws[L.zl + i] + alpha_dual * dzl;
+          z = fmax(fmin(z, 1e10 * mu / sl), mu / (1e10 * sl));
+          ws[L.zl + i] = z;
+        }
+        if (b.hasu) {
+          const double su = b.hi - wi;
+          double z = ws[L.zu + i] + alpha_dual * dzu;
+          z = fmax(fmin(z, 1e10 * mu / su), mu / (1e10 * su));
+          ws[L.zu + i] = z;
+        }
+      }
+      if (!SINGLE)
+        for (int i = g.lane; i < L.m; i += LANES) ws[L.lam + i] += alpha * (ws[L.lamp + i] - ws[L.lam + i]);
+      g.sync();
+      sync_blocked();
+      eval_derivatives(true);
+    }
+    info.iters = iter;
+    info.f = f_curr / df;
+    info.df = df;
+    return info;
+  }
+
+  // SOC bookkeeping: the plain step (d, lamp) is parked in the (dead until the next iteration)
+  // Riccati gain-free region?  No region is dead: K, P are needed for the re-solve.  Park it in
+  // grad?  grad is live (rhs).  -> dedicated scratch: reuse `c`-sized `lamp` is live too.  We park in
+  // the Hessian block storage, which is not read again until the next factorisation.
+  MPCV_D void save_step() const {
+    for (int i = g.lane; i < L.n; i += LANES) ws[L.hw + i] = ws[L.d + i];
+    for (int i = g.lane; i < L.m; i += LANES) ws[L.hw + L.n + i] = ws[L.lamp + i];
+    g.sync();
+  }
+  MPCV_D void restore_step() const {
+    for (int i = g.lane; i < L.n; i += LANES) ws[L.d + i] = ws[L.hw + i];
+    for (int i = g.lane; i < L.m; i += LANES) ws[L.lamp + i] = ws[L.hw + L.n + i];
+    g.sync();
+  }
+  // trial evaluation for the SOC loop: c_soc <- c(x + alpha_soc d_soc) + alpha_soc * c_soc, in place in ct
+  MPCV_DN void eval_trial_soc(double alpha_soc, double* f_out, double* theta_out, double* phi_out) const {
+    double fpart = 0.0, thpart = 0.0, logpart = 0.0;
+    bool bad = false;
+    for (int k = g.lane; k < N; k += LANES) {
+      double x[NX], u[NU], xn[NX], q;
+      load_xu(k, L.w, alpha_soc, L.d, x, u);
+      Model::val(P, x, u, pg(), ps(k), xn, &q);
+      fpart += q;
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        const double r = xn[i] - (ws[L.w + ix(k + 1, i)] + alpha_soc * ws[L.d + ix(k + 1, i)]);
+        thpart += fabs(r);
+        ws[L.ct + (k + 1) * NX + i] = r + alpha_soc * ws[L.ct + (k + 1) * NX + i];
+      }
+    }
+    if (g.lane == 0) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) {
+        const double r = ws[L.par + i] - (ws[L.w + ix(0, i)] + alpha_soc * ws[L.d + ix(0, i)]);
+        thpart += fabs(r);
+        ws[L.ct + i] = r + alpha_soc * ws[L.ct + i];
+      }
+    }
+    for (int i = g.lane; i < L.n; i += LANES) {
+      const Bnd b = bnd(i);
+      if (b.hasl || b.hasu) {
+        const double v = ws[L.w + i] + alpha_soc * ws[L.d + i];
+        if (b.hasl) { const double s = v - b.lo; if (!(s > 0.0)) bad = true; logpart += log(s); }
+        if (b.hasu) { const double s = b.hi - v; if (!(s > 0.0)) bad = true; logpart += log(s); }
+      }
+    }
+    const double f = df * g.sum(fpart);
+    const double lg = g.sum(logpart);
+    const bool anybad = g.max(bad ? 1.0 : 0.0) > 0.0;
+    *f_out = f;
+    *theta_out = g.sum(thpart);
+    *phi_out = anybad ? INFINITY : f - mu * lg;
+    g.sync();
+  }
+
+  // ---- export (projection into the ORIGINAL bounds: honor_original_bounds=yes) -------------------------
+  MPCV_D double projected(int i) const {
+    double v = ws[L.w + i];
+    const double l = lbx[i], u = ubx[i];
+    if (l > -kInfBound) v = fmax(v, l);
+    if (u < kInfBound) v = fmin(v, u);
+    return v;
+  }
+};
+
+}  // namespace mpcv

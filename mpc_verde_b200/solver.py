@@ -1,0 +1,319 @@
+"""Host-side mirror of the reference's solver interface, with a leading batch dimension.
+
+Reference call shape kept (Casadi/multiple_shooting_casadi.py:181-242):
+
+    solver = nlpsol('solver', 'ipopt', nlp_prob, opts)          # nlp_prob = {'f','x','g','p'}
+    sol = solver(x0=..., lbx=..., ubx=..., lbg=..., ubg=..., p=...)
+    sol['x'], sol['f']                                           # (+ 'g','lam_x','lam_g')
+    solver.stats()['return_status']
+
+`nlp_prob` is a structural template (problems.py) instead of a CasADi SX graph: the GPU
+solver is a fixed-structure solver for the shooting transcriptions of the scripts.  Every
+array argument takes a leading batch dimension B; a call without one solves a single problem
+and returns unbatched results, exactly like the scripts.
+
+PyTorch is used for device memory and streams only; all compute is in libmpcv.so.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from .spec import (LAYOUT_AUTO, SHOOTING_SINGLE, STATUS_NAMES, WARM_SHIFT, Spec, ipopt_defaults)
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class _Handle:
+    def __init__(self, spec):
+        self.lib = _lib.lib()
+        self.spec = spec
+        self.h = self.lib.mpcv_create(C.byref(spec))
+        if not self.h:
+            msg = self.lib.mpcv_last_error()
+            raise _lib.MpcvError("mpcv_create failed: %s" % (msg.decode() if msg else "?"))
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.mpcv_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class NlpSolver:
+    """Callable returned by `nlpsol`; mirrors the CasADi `Function` the scripts call."""
+
+    def __init__(self, name, prob, opts=None, device=None):
+        if not (isinstance(prob, dict) and "spec" in prob):
+            raise TypeError("nlp_prob must come from mpc_verde_b200.problems (keys 'f','x','g','p','spec')")
+        self.name = name
+        self.prob = prob
+        spec = prob["spec"].copy()
+        ipopt_defaults(spec, opts)
+        if opts and "layout" in opts:
+            spec.layout = opts["layout"]
+        self.spec = spec
+        if not torch.cuda.is_available():
+            raise _lib.MpcvError("mpc_verde_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        with torch.cuda.device(self.device):
+            self._handle = _Handle(spec)
+        self._last = None
+        self._latency = None
+
+    # -- sizes ---------------------------------------------------------------------------
+    @property
+    def n_var(self):
+        return self.spec.n_var
+
+    @property
+    def n_g(self):
+        return self.spec.n_g
+
+    @property
+    def n_p(self):
+        return self.spec.n_p
+
+    def launch_count(self):
+        return int(self._handle.lib.mpcv_launch_count(self._handle.h))
+
+    # -- argument normalisation ---------------------------------------------------------------
+    def _vec(self, a, n, fill, name, device):
+        """bounds: scalar-broadcast allowed (e.g. lbg=-inf, single_shooting_v1.py:141)."""
+        if a is None:
+            a = fill
+        if isinstance(a, torch.Tensor):
+            t = a.to(dtype=torch.float64).reshape(-1)
+        else:
+            t = torch.as_tensor(np.asarray(a, dtype=np.float64).reshape(-1))
+        if t.numel() == 1:
+            t = t.expand(n)
+        if t.numel() != n:
+            raise ValueError("%s has %d entries, expected %d" % (name, t.numel(), n))
+        return t.contiguous().to(device)
+
+    def _batched(self, a, n, name):
+        if isinstance(a, torch.Tensor):
+            t = a.to(dtype=torch.float64)
+        else:
+            t = torch.as_tensor(np.asarray(a, dtype=np.float64))
+        if t.dim() == 2 and t.shape[1] == 1 and n != 1:
+            t = t.reshape(-1)           # CasADi column vector
+        if t.dim() <= 1:
+            if t.numel() == 1 and n != 1:
+                t = t.reshape(1).expand(n)
+            t = t.reshape(1, -1)
+            unbatched = True
+        else:
+            unbatched = False
+        if t.shape[-1] != n:
+            raise ValueError("%s has trailing size %d, expected %d" % (name, t.shape[-1], n))
+        return t.reshape(-1, n), unbatched
+
+    def _check_g_bounds(self, lbg, ubg):
+        """The transcription fixes the g-bounds: 0 for the defect rows of multiple shooting
+        (multiple_shooting_casadi.py:135-136,174-175), +-inf for the inert rows of single
+        shooting (single_shooting_v1.py:141-142).  Anything else is outside the hot path."""
+        for b, sign, nm in ((lbg, -1, "lbg"), (ubg, +1, "ubg")):
+            if b is None:
+                continue
+            v = np.asarray(b.cpu() if isinstance(b, torch.Tensor) else b, dtype=np.float64).reshape(-1)
+            if self.spec.single:
+                ok = np.all(v * sign >= 1e19)
+            else:
+                ok = np.all(v == 0.0)
+            if not ok:
+                raise NotImplementedError(
+                    "%s: only the scripts' own constraint bounds are supported (0 for multiple-shooting defects, "
+                    "+-inf for single-shooting rows)" % nm)
+
+    # -- the solve -------------------------------------------------------------------------------
+    def __call__(self, x0=None, lbx=None, ubx=None, lbg=None, ubg=None, p=None, lam_x0=None, lam_g0=None):
+        if p is None:
+            raise ValueError("p is required")
+        self._check_g_bounds(lbg, ubg)
+        n, ng, npar = self.spec.n_var, self.spec.n_g, self.spec.n_p
+        on_device = isinstance(p, torch.Tensor) and p.is_cuda
+        pt, unb = self._batched(p, npar, "p")
+        B = pt.shape[0]
+        if x0 is None:
+            x0t = None
+        else:
+            x0t, _ = self._batched(x0, n, "x0")
+            if x0t.shape[0] == 1 and B > 1:
+                x0t = x0t.expand(B, n)
+            if x0t.shape[0] != B:
+                raise ValueError("x0 batch %d != p batch %d" % (x0t.shape[0], B))
+        lib, h = self._handle.lib, self._handle.h
+        if on_device:
+            dev = pt.device
+            with torch.cuda.device(dev):
+                pt = pt.contiguous()
+                x0d = None if x0t is None else x0t.to(dev).contiguous()
+                lb = self._vec(lbx, n, -math.inf, "lbx", dev)
+                ub = self._vec(ubx, n, math.inf, "ubx", dev)
+                out = {
+                    "x": torch.empty((B, n), dtype=torch.float64, device=dev),
+                    "f": torch.empty((B,), dtype=torch.float64, device=dev),
+                    "g": torch.empty((B, ng), dtype=torch.float64, device=dev),
+                    "lam_g": torch.empty((B, ng), dtype=torch.float64, device=dev),
+                    "lam_x": torch.empty((B, n), dtype=torch.float64, device=dev),
+                }
+                status = torch.empty((B,), dtype=torch.int32, device=dev)
+                iters = torch.empty((B,), dtype=torch.int32, device=dev)
+                stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+                rc = lib.mpcv_solve(h, _ptr(x0d), _ptr(lb), _ptr(ub), _ptr(pt), _ptr(out["x"]), _ptr(out["f"]),
+                                    _ptr(out["g"]), _ptr(out["lam_g"]), _ptr(out["lam_x"]), _ptr(status), _ptr(iters),
+                                    C.c_int64(B), stream)
+                _lib.check(rc, "mpcv_solve")
+        else:
+            # host buffers: one C-ABI call does H2D (pinned staging), solve, D2H
+            pt = np.ascontiguousarray(pt.numpy())
+            x0h = None if x0t is None else np.ascontiguousarray(x0t.numpy())
+            lb = np.ascontiguousarray(self._vec(lbx, n, -math.inf, "lbx", "cpu").numpy())
+            ub = np.ascontiguousarray(self._vec(ubx, n, math.inf, "ubx", "cpu").numpy())
+            out = {"x": np.empty((B, n)), "f": np.empty((B,)), "g": np.empty((B, ng)), "lam_g": np.empty((B, ng)),
+                   "lam_x": np.empty((B, n))}
+            status = np.empty((B,), np.int32)
+            iters = np.empty((B,), np.int32)
+            hp = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
+            with torch.cuda.device(self.device):
+                rc = lib.mpcv_solve_host(h, hp(x0h), hp(lb), hp(ub), hp(pt), hp(out["x"]), hp(out["f"]), hp(out["g"]),
+                                         hp(out["lam_g"]), hp(out["lam_x"]), hp(status), hp(iters), C.c_int64(B))
+            _lib.check(rc, "mpcv_solve_host")
+        self._last = (status, iters)
+        if unb:
+            out = {k: v[0] for k, v in out.items()}
+        return out
+
+    def stats(self):
+        """Like CasADi's solver.stats(): per-problem `return_status`, `iter_count`, `success`."""
+        if self._last is None:
+            return {}
+        status, iters = self._last
+        st = status.cpu().numpy() if isinstance(status, torch.Tensor) else status
+        it = iters.cpu().numpy() if isinstance(iters, torch.Tensor) else iters
+        names = [STATUS_NAMES.get(int(s), "Internal_Error") for s in st]
+        return {"return_status": names if len(names) > 1 else names[0], "status_code": st,
+                "iter_count": it if len(it) > 1 else int(it[0]), "success": bool(np.all(st == 0))}
+
+    # -- latency capture (p50 solve us) ---------------------------------------------------------------
+    def enable_latency(self, B):
+        self._latency = torch.zeros((B,), dtype=torch.int64, device=self.device)
+        _lib.check(self._handle.lib.mpcv_set_latency_buffer(self._handle.h, _ptr(self._latency)), "set_latency")
+        return self._latency
+
+    def disable_latency(self):
+        _lib.check(self._handle.lib.mpcv_set_latency_buffer(self._handle.h, None), "set_latency")
+        self._latency = None
+
+    # -- rollout F / ff -------------------------------------------------------------------------------
+    def rollout(self, p, U):
+        """Shooting rollout of a control sequence (ff(U,P), single_shooting_v1.py:95; the F loop
+        of single_shooting_v2.py:222-224).  Returns X [B, N+1, nx] and the accumulated cost q [B]."""
+        s = self.spec
+        pt, unb = self._batched(p, s.n_p, "p")
+        Ut, _ = self._batched(U, s.nu * s.N, "U")
+        B = pt.shape[0]
+        dev = self.device
+        with torch.cuda.device(dev):
+            pd, Ud = pt.to(dev).contiguous(), Ut.to(dev).contiguous()
+            X = torch.empty((B, s.N + 1, s.nx), dtype=torch.float64, device=dev)
+            q = torch.empty((B,), dtype=torch.float64, device=dev)
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(self._handle.lib.mpcv_rollout(self._handle.h, _ptr(pd), _ptr(Ud), _ptr(X), _ptr(q),
+                                                     C.c_int64(B), stream), "mpcv_rollout")
+        if not (isinstance(p, torch.Tensor) and p.is_cuda):
+            X, q = X.cpu().numpy(), q.cpu().numpy()
+        return (X[0], q[0]) if unb else (X, q)
+
+    def stage_derivs(self, z, pstage, lam):
+        """Hand-written stage sweeps (value, A, B, gradient, Hessian of q + lam'phi) for parity tests."""
+        s = self.spec
+        nz = s.nx + s.nu
+        dev = self.device
+        zt = torch.as_tensor(np.asarray(z, dtype=np.float64)).reshape(-1, nz).to(dev).contiguous()
+        B = zt.shape[0]
+        npp = max(s.npg + s.nps, 1)
+        pt = torch.zeros((B, npp), dtype=torch.float64) if pstage is None else torch.as_tensor(np.asarray(pstage, dtype=np.float64)).reshape(B, -1)
+        pt = pt.to(dev).contiguous()
+        lt = torch.as_tensor(np.asarray(lam, dtype=np.float64)).reshape(B, s.nx).to(dev).contiguous()
+        mk = lambda *shape: torch.empty(shape, dtype=torch.float64, device=dev)
+        out = {"xn": mk(B, s.nx), "A": mk(B, s.nx, s.nx), "B": mk(B, s.nx, s.nu), "q": mk(B), "grad": mk(B, nz),
+               "H": mk(B, nz, nz)}
+        with torch.cuda.device(dev):
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            _lib.check(self._handle.lib.mpcv_stage_derivs(self._handle.h, _ptr(zt), _ptr(pt), _ptr(lt), _ptr(out["xn"]),
+                                                          _ptr(out["A"]), _ptr(out["B"]), _ptr(out["q"]), _ptr(out["grad"]),
+                                                          _ptr(out["H"]), C.c_int64(B), stream), "mpcv_stage_derivs")
+        return {k: v.cpu().numpy() for k, v in out.items()}
+
+    # -- batched closed loop ---------------------------------------------------------------------------
+    def closed_loop(self, x_init, pglob=None, ptraj=None, lbx=None, ubx=None, n_steps=100, warm_mode=WARM_SHIFT,
+                    stop_radius=0.0):
+        """The scripts' MPC loop, batched and on device: solve -> apply u0 -> plant step with the
+        same discretisation -> shifted guess (multiple_shooting_casadi.py:224-298,
+        single_shooting_v1.py:164-214).  Returns the histories the scripts keep
+        (states [B, n_steps+1, nx], applied controls [B, n_steps, nu]) plus per-problem
+        step / iteration counts and the first non-zero solver status."""
+        s = self.spec
+        dev = self.device
+        to_np = not (isinstance(x_init, torch.Tensor) and x_init.is_cuda)
+        xi, unb = self._batched(x_init, s.nx, "x_init")
+        B = xi.shape[0]
+        with torch.cuda.device(dev):
+            xi = xi.to(dev).contiguous()
+            pg = None
+            if s.npg > 0:
+                pg, _ = self._batched(pglob, s.npg, "pglob")
+                pg = pg.expand(B, s.npg).to(dev).contiguous()
+            pt = None
+            if s.nps > 0:
+                pt = ptraj if isinstance(ptraj, torch.Tensor) else torch.as_tensor(np.asarray(ptraj, dtype=np.float64))
+                pt = pt.to(dtype=torch.float64)
+                if pt.dim() == 2:
+                    pt = pt.unsqueeze(0)
+                if pt.shape[1] != n_steps + s.N or pt.shape[2] != s.nps:
+                    raise ValueError("ptraj must be [B, n_steps+N, nps] = [*, %d, %d]" % (n_steps + s.N, s.nps))
+                pt = pt.expand(B, -1, -1).to(dev).contiguous()
+            lb = self._vec(lbx, s.n_var, -math.inf, "lbx", dev)
+            ub = self._vec(ubx, s.n_var, math.inf, "ubx", dev)
+            states = torch.empty((B, n_steps + 1, s.nx), dtype=torch.float64, device=dev)
+            controls = torch.empty((B, n_steps, s.nu), dtype=torch.float64, device=dev)
+            steps = torch.empty((B,), dtype=torch.int32, device=dev)
+            iters = torch.empty((B,), dtype=torch.int32, device=dev)
+            status = torch.empty((B,), dtype=torch.int32, device=dev)
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            rc = self._handle.lib.mpcv_closed_loop(self._handle.h, _ptr(xi), _ptr(pg), _ptr(pt), _ptr(lb), _ptr(ub),
+                                                   C.c_int32(n_steps), C.c_int32(warm_mode), C.c_double(stop_radius),
+                                                   _ptr(states), _ptr(controls), _ptr(steps), _ptr(iters), _ptr(status),
+                                                   C.c_int64(B), stream)
+            _lib.check(rc, "mpcv_closed_loop")
+        out = {"states": states, "controls": controls, "steps": steps, "iters": iters, "status": status}
+        if to_np:
+            out = {k: v.cpu().numpy() for k, v in out.items()}
+        return out
+
+
+def nlpsol(name, plugin, nlp_prob, opts=None, device=None):
+    """Drop-in for `ca.nlpsol(name, 'ipopt', nlp_prob, opts)` (single_shooting_v1.py:131,
+    single_shooting_v2.py:177, multiple_shooting_casadi.py:197)."""
+    if plugin != "ipopt":
+        raise ValueError("only the 'ipopt' plugin of the reference scripts is provided (got %r)" % (plugin,))
+    return NlpSolver(name, nlp_prob, opts, device)
+
+
+def fp64_peak(device=None):
+    """Measured FP64 FMA peak (TFLOP/s) of the current GPU: the roofline denominator."""
+    lib = _lib.lib()
+    t, ms = C.c_double(0), C.c_double(0)
+    with torch.cuda.device(device if device is not None else torch.cuda.current_device()):
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _lib.check(lib.mpcv_fp64_peak(C.byref(t), C.byref(ms), stream), "mpcv_fp64_peak")
+    return t.value, ms.value

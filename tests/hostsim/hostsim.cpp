@@ -1,0 +1,110 @@
+// hostsim.cpp — DEVELOPMENT HARNESS, not a product path and not a fallback.
+// Compiles the device headers (mpcv_models.cuh / mpcv_ipm.cuh / mpcv_driver.cuh) as plain
+// C++ with one lane per problem so that the interior-point logic can be unit-tested against
+// the oracle in a container without a GPU.  Nothing in mpc_verde_b200/ loads this library;
+// the shipped library (libmpcv.so) contains CUDA kernels only and errors out without a GPU.
+#include <cstring>
+#include <vector>
+
+#include "../../mpc_verde_b200/csrc/mpcv_driver.cuh"
+#include "../../mpc_verde_b200/csrc/mpcv_params.h"
+
+using namespace mpcv;
+
+template <class Model, bool SINGLE>
+static int hs_solve_t(const mpcv_spec* s, const SolveIO& io, long B) {
+  Params P = params_from_spec(*s);
+  Layout L = make_layout<Model, SINGLE>(s->N);
+  std::vector<double> buf(L.total);
+  for (long b = 0; b < B; ++b) {
+    std::fill(buf.begin(), buf.end(), 0.0);
+    solve_problem<Model, SINGLE, 1, WsDense>(P, L, WsDense{buf.data()}, Grp<1>(0), io, b);
+  }
+  return 0;
+}
+
+template <class Model, bool SINGLE>
+static int hs_loop_t(const mpcv_spec* s, const LoopIO& io, long B) {
+  Params P = params_from_spec(*s);
+  Layout L = make_layout<Model, SINGLE>(s->N);
+  std::vector<double> buf(L.total);
+  for (long b = 0; b < B; ++b) {
+    std::fill(buf.begin(), buf.end(), 0.0);
+    closed_loop_problem<Model, SINGLE, 1, WsDense>(P, L, WsDense{buf.data()}, Grp<1>(0), io, b);
+  }
+  return 0;
+}
+
+template <class Model>
+static int hs_der_t(const mpcv_spec* s, const double* z, const double* pstage, const double* lam, double* xn,
+                    double* A, double* Bm, double* q, double* grad, double* H, long B) {
+  constexpr int NX = Model::NX, NU = Model::NU, NZ = NX + NU, NW = NZ * (NZ + 1) / 2;
+  Params P = params_from_spec(*s);
+  for (long b = 0; b < B; ++b) {
+    const double* pp = pstage + b * (Model::NPG + Model::NPS);
+    double W[NW], xv[NX], qv;
+    Model::der(P, z + b * NZ, z + b * NZ + NX, pp, pp + Model::NPG, lam + b * NX, 1.0, true, xn + b * NX,
+               A + b * NX * NX, Bm + b * NX * NU, q + b, grad + b * NZ, W);
+    for (int i = 0; i < NZ; ++i)
+      for (int j = 0; j < NZ; ++j) H[b * NZ * NZ + i * NZ + j] = i >= j ? W[tri(i, j)] : W[tri(j, i)];
+    // value-only path must agree with the derivative path
+    Model::val(P, z + b * NZ, z + b * NZ + NX, pp, pp + Model::NPG, xv, &qv);
+    for (int i = 0; i < NX; ++i)
+      if (xv[i] != xn[b * NX + i] && !(fabs(xv[i] - xn[b * NX + i]) <= 1e-13 * (1 + fabs(xv[i])))) return -1;
+    if (!(fabs(qv - q[b]) <= 1e-12 * (1 + fabs(qv)))) return -2;
+  }
+  return 0;
+}
+
+#define HS_DISPATCH(s, SINGLE_OK, CALL)                                                        \
+  switch ((s)->model) {                                                                        \
+    case MPCV_MODEL_UNICYCLE_RK4_QUAD: return CALL(Unicycle<0>);                               \
+    case MPCV_MODEL_UNICYCLE_EULER_NODE: return CALL(Unicycle<1>);                             \
+    case MPCV_MODEL_UNICYCLE_RK4_NODE: return CALL(Unicycle<2>);                               \
+    case MPCV_MODEL_LINEAR3: return CALL(Linear<3 HS_COMMA false>);                            \
+    case MPCV_MODEL_LINEAR4: return CALL(Linear<4 HS_COMMA false>);                            \
+    case MPCV_MODEL_LINEAR4_DU: return CALL(Linear<4 HS_COMMA true>);                          \
+    case MPCV_MODEL_LINEAR3_DU: return CALL(Linear<3 HS_COMMA true>);                          \
+    default: return -22;                                                                       \
+  }
+#define HS_COMMA ,
+
+extern "C" {
+
+int hs_solve(const mpcv_spec* s, const double* x0, const double* lbx, const double* ubx, const double* p,
+             double* x, double* f, double* g, double* lam_g, double* lam_x, int* status, int* iters, long B) {
+  SolveIO io{x0, lbx, ubx, p, x, f, g, lam_g, lam_x, status, iters, nullptr};
+  if (s->shooting == MPCV_SHOOTING_SINGLE) {
+#define CALL(M) hs_solve_t<M, true>(s, io, B)
+    HS_DISPATCH(s, 1, CALL)
+#undef CALL
+  } else {
+#define CALL(M) hs_solve_t<M, false>(s, io, B)
+    HS_DISPATCH(s, 1, CALL)
+#undef CALL
+  }
+}
+
+int hs_closed_loop(const mpcv_spec* s, const double* x_init, const double* pglob, const double* ptraj,
+                   const double* lbx, const double* ubx, int n_steps, int warm_mode, double stop_radius,
+                   double* out_states, double* out_controls, int* out_steps, int* out_iters, int* out_status, long B) {
+  LoopIO io{x_init, pglob, ptraj, lbx, ubx, out_states, out_controls, out_steps, out_iters, out_status,
+            n_steps, warm_mode, stop_radius};
+  if (s->shooting == MPCV_SHOOTING_SINGLE) {
+#define CALL(M) hs_loop_t<M, true>(s, io, B)
+    HS_DISPATCH(s, 1, CALL)
+#undef CALL
+  } else {
+#define CALL(M) hs_loop_t<M, false>(s, io, B)
+    HS_DISPATCH(s, 1, CALL)
+#undef CALL
+  }
+}
+
+int hs_stage_derivs(const mpcv_spec* s, const double* z, const double* pstage, const double* lam, double* xn,
+                    double* A, double* Bm, double* q, double* grad, double* H, long B) {
+#define CALL(M) hs_der_t<M>(s, z, pstage, lam, xn, A, Bm, q, grad, H, B)
+  HS_DISPATCH(s, 1, CALL)
+#undef CALL
+}
+}

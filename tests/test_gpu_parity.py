@@ -1,0 +1,337 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (ctypes), against the CPU
+oracle on the same seeded inputs, against the reference's golden files, and through
+size-independent properties at BASELINE.json's full sizes.
+
+Tolerances are those of BASELINE.json's north star:
+  RK4 rollout 1e-12 relative; optimal controls 1e-5 absolute; cost 1e-6 relative;
+  closed-loop states 1e-4.  (Observed differences are many orders tighter; the asserts use the
+  stated bars, and a few use tighter ones where bit-level agreement of the iteration path is
+  the point.)
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from mpc_verde_b200 import problems
+from mpc_verde_b200 import spec as S
+from oracle import mpc_oracle as O
+from tests import common
+
+pytestmark = pytest.mark.gpu
+
+NCPU = os.cpu_count() or 1
+
+
+@pytest.fixture(scope="module")
+def mv():
+    import mpc_verde_b200 as m
+    return m
+
+
+def _solver(mv, prob, **opts):
+    return mv.nlpsol("solver", "ipopt", prob, {"ipopt": {"max_iter": 2000, "print_level": 0,
+                                                          "acceptable_tol": 1e-8,
+                                                          "acceptable_obj_change_tol": 1e-6}, "print_time": 0, **opts})
+
+
+# ---- T1: RK4 rollout -------------------------------------------------------------------------
+def test_rollout_known_answer_and_golden_replay(mv):
+    solver = _solver(mv, problems.unicycle_multiple_shooting())
+    X, q = solver.rollout(np.array([0, 0, 0, 10, 10, 0.0]), np.tile([1.0, math.pi / 4], 10))
+    assert np.allclose(X[1], [0.1991785472131909, 0.01567569162852597, 0.1570796326794897], rtol=1e-13, atol=0)
+    g = common.golden("unicycle_ms_1exemplo.csv")
+    # q[r+1] = F(q[r], w[r-1]) for r >= 1: batch all 83 single steps
+    xs, us = g[1:84, 0:3], g[0:83, 3:5]
+    p = np.concatenate([xs, np.tile([10, 10, 0.0], (83, 1))], 1)
+    U = np.tile(us, (1, 10))
+    Xb, _ = solver.rollout(p, U)
+    err = np.abs(Xb[:, 1, :] - g[2:85, 0:3]).max()
+    assert err <= 1e-12 * max(1.0, np.abs(g[:, 0:3]).max())
+
+
+def test_rollout_matches_oracle_random(mv):
+    rng = np.random.default_rng(3)
+    for prob in (problems.unicycle_multiple_shooting(), problems.unicycle_single_shooting_euler(),
+                 problems.unicycle_tracking(N=20, T=0.05, M=1)):
+        solver = _solver(mv, prob)
+        sp = solver.spec
+        B = 512
+        p = rng.normal(size=(B, sp.n_p)) * 3
+        U = rng.uniform(-1, 1, size=(B, sp.nu * sp.N))
+        X, q = solver.rollout(p, U)
+        Xo, qo = O.rollout(sp, p, U)
+        assert np.abs(X - Xo).max() <= 1e-12 * (1 + np.abs(Xo).max())
+        assert np.abs(q - qo).max() <= 1e-12 * (1 + np.abs(qo).max())
+
+
+# ---- hand-written stage sweeps vs the oracle's generic AD ------------------------------------------
+@pytest.mark.parametrize("mk", [
+    lambda: problems.unicycle_multiple_shooting(),
+    lambda: problems.unicycle_single_shooting_euler(),
+    lambda: problems.unicycle_tracking(M=1),
+    lambda: problems.unicycle_tracking(M=3),
+    lambda: problems.linear_tracking(3, 5, (10, 1, 0.5, 0), 0.01),
+    lambda: problems.linear_tracking(4, 5, (1, 2, 3, 4), 1.0),
+    lambda: problems.linear_tracking(4, 5, (1.44, 0, 1, 0), 0.0, R1=1e-4),
+    lambda: problems.linear_tracking(3, 5, (10, 1, 0, 0), 0.01, R1=0.5),
+])
+def test_stage_derivatives_vs_oracle_ad(mv, mk):
+    solver = _solver(mv, mk())
+    sp = solver.spec
+    rng = np.random.default_rng(1)
+    B = 256
+    z = rng.normal(size=(B, sp.nx + sp.nu)) * 2
+    ps = rng.normal(size=(B, max(sp.npg + sp.nps, 1)))
+    lam = rng.normal(size=(B, sp.nx)) * 3
+    a = O.stage_derivs(sp, z, ps, lam)
+    b = solver.stage_derivs(z, ps, lam)
+    for k in a:
+        assert np.abs(a[k] - b[k]).max() <= 1e-12 * (1 + np.abs(a[k]).max()), k
+
+
+# ---- T3/T9: batched solve vs oracle ------------------------------------------------------------------
+def _compare_solve(solver, sp, w0, lbx, ubx, p, on_device):
+    import torch
+    if on_device:
+        sol = solver(x0=torch.as_tensor(w0).cuda(), lbx=lbx, ubx=ubx, p=torch.as_tensor(p).cuda())
+        sol = {k: v.cpu().numpy() for k, v in sol.items()}
+    else:
+        sol = solver(x0=w0, lbx=lbx, ubx=ubx, p=p)
+    st = solver.stats()
+    ref = O.solve(sp, w0, lbx, ubx, p, nthreads=NCPU)
+    assert np.all(ref["status"] == 0)
+    assert st["success"], np.unique(st["status_code"], return_counts=True)
+    # iteration path identical except where libm-vs-libdevice ulps flip a decision
+    assert np.mean(st["iter_count"] == ref["iters"]) >= 0.98
+    assert np.abs(sol["x"] - ref["x"]).max() <= 1e-5          # controls/states, north-star bar
+    assert np.abs(sol["f"] - ref["f"]).max() <= 1e-6 * np.abs(ref["f"]).max()
+    same = st["iter_count"] == ref["iters"]
+    assert np.abs(sol["x"][same] - ref["x"][same]).max() <= 1e-9
+    assert np.abs(sol["lam_g"][same] - ref["lam_g"][same]).max() <= 1e-7 * (1 + np.abs(ref["lam_g"]).max())
+    return sol, ref
+
+
+@pytest.mark.parametrize("on_device", [True, False])
+def test_unicycle_ms_batch_vs_oracle(mv, on_device):
+    solver = _solver(mv, problems.unicycle_multiple_shooting())
+    sp = solver.spec
+    x0s, p = common.unicycle_batch(2048)
+    lbx, ubx = problems.unicycle_bounds(sp, x_box=20.0)
+    w0 = problems.cold_start(sp, x0s)
+    _compare_solve(solver, sp, w0, lbx, ubx, p, on_device)
+
+
+def test_unicycle_ms_first_solve_known_answer(mv):
+    solver = _solver(mv, problems.unicycle_multiple_shooting())
+    lbx, ubx = problems.unicycle_bounds(solver.spec)
+    sol = solver(x0=np.zeros(53), lbx=lbx, ubx=ubx, lbg=0, ubg=0, p=[0, 0, 0, 10, 10, 0])
+    assert solver.stats()["return_status"] == "Solve_Succeeded"
+    assert solver.stats()["iter_count"] == 18
+    assert sol["x"][3] == 1.0 and sol["x"][4] == math.pi / 4        # projected onto the original box
+    assert abs(sol["f"] - 1081.5439729) <= 1e-6 * 1081.5439729
+
+
+def test_unicycle_ms_warp_layout_equals_thread_layout(mv):
+    x0s, p = common.unicycle_batch(300, seed=5)
+    out = []
+    for layout in (S.LAYOUT_THREAD, S.LAYOUT_WARP):
+        solver = _solver(mv, problems.unicycle_multiple_shooting(), layout=layout)
+        sp = solver.spec
+        lbx, ubx = problems.unicycle_bounds(sp, x_box=20.0)
+        sol = solver(x0=problems.cold_start(sp, x0s), lbx=lbx, ubx=ubx, p=p)
+        assert solver.stats()["success"]
+        out.append((sol, solver.stats()["iter_count"]))
+    assert np.mean(out[0][1] == out[1][1]) >= 0.98
+    assert np.abs(out[0][0]["x"] - out[1][0]["x"]).max() <= 1e-7
+
+
+def test_single_shooting_batch_vs_oracle_and_ms_equivalence(mv):
+    x0s, p = common.unicycle_batch(512, seed=11)
+    ss = _solver(mv, problems.unicycle_single_shooting_rk4())
+    lb, ub = problems.unicycle_bounds(ss.spec)
+    sol_ss, _ = _compare_solve(ss, ss.spec, np.zeros((512, 20)), lb, ub, p, True)
+    ms = _solver(mv, problems.unicycle_multiple_shooting())
+    lbm, ubm = problems.unicycle_bounds(ms.spec)
+    sol_ms = ms(x0=problems.cold_start(ms.spec, x0s), lbx=lbm, ubx=ubm, p=p)
+    u_ms = sol_ms["x"].reshape(512, -1)[:, :50].reshape(512, 10, 5)[:, :, 3:5].reshape(512, 20)
+    # the difference.py idea: single and multiple shooting share the optimum (when they land in
+    # the same local minimum, which the costs tell)
+    same = np.abs(sol_ms["f"] - sol_ss["f"]) <= 1e-7 * np.abs(sol_ss["f"])
+    assert same.mean() > 0.9
+    assert np.abs(u_ms[same] - sol_ss["x"][same]).max() <= 1e-5
+    eu = _solver(mv, problems.unicycle_single_shooting_euler())
+    _compare_solve(eu, eu.spec, np.zeros((512, 20)), lb, ub, p, True)
+
+
+def test_unicycle_tracking_batch_vs_oracle(mv):
+    solver = _solver(mv, problems.unicycle_tracking(N=20, T=0.05, M=1))
+    sp = solver.spec
+    rng = np.random.default_rng(4)
+    B = 512
+    t = np.arange(sp.N) * sp.T
+    x0 = np.stack([1 + rng.normal(size=B) * 0.1, rng.normal(size=B) * 0.1, math.pi / 2 + rng.normal(size=B) * 0.1], 1)
+    stage = np.stack([np.cos(0.1 * t), np.sin(0.1 * t), math.pi / 2 + 0.1 * t, np.ones_like(t) * 0.1, np.ones_like(t) * 0.1], 1)
+    p = np.concatenate([x0, np.tile(stage.ravel(), (B, 1))], 1)
+    lbx, ubx = problems.control_box(sp, (-1, -math.pi / 4), (1, math.pi / 4), (-20, -2, -np.inf), (20, 2, np.inf))
+    _compare_solve(solver, sp, problems.cold_start(sp, x0), lbx, ubx, p, True)
+
+
+@pytest.mark.parametrize("layout", [S.LAYOUT_THREAD, S.LAYOUT_WARP])
+def test_pendulum_batch_vs_oracle(mv, layout):
+    sp0, lbx, ubx, pglob, _, _ = common.pendulum_setup(N=40, ntu=0, discretisation="rk4")
+    solver = _solver(mv, {"spec": sp0}, layout=layout)
+    sp = solver.spec
+    x0, p = common.pendulum_batch(sp, pglob, 256)
+    _compare_solve(solver, sp, problems.cold_start(sp, x0), lbx, ubx, p, True)
+
+
+@pytest.mark.parametrize("layout", [S.LAYOUT_THREAD, S.LAYOUT_WARP])
+def test_dynamic_bicycle_n50_vs_oracle(mv, layout):
+    N, dt, B = 50, 0.05, 128
+    rng = np.random.default_rng(7)
+    prob = problems.linear_tracking(4, N, Q=(1, 1, 1, 1), R=1.0, T=dt)
+    solver = _solver(mv, prob, layout=layout)
+    sp = solver.spec
+    lbx, ubx = problems.control_box(sp, -20.0, 20.0)
+    ps = []
+    x0 = rng.normal(size=(B, 4)) * np.array([0.2, 0.05, 0.1, 0.05])
+    for b in range(B):
+        Ac, Bc = problems.dynamic_bicycle_matrices(rng.uniform(0.4, 0.8))
+        A, Bd = problems.c2d(Ac, Bc, dt)
+        stage = np.zeros((N, 5))
+        stage[:, 0] = np.linspace(0, 1, N) * rng.uniform(0.5, 1.5)
+        ps.append(np.concatenate([x0[b], A.ravel(), Bd.ravel(), stage.ravel()]))
+    p = np.array(ps)
+    _compare_solve(solver, sp, problems.cold_start(sp, x0), lbx, ubx, p, True)
+
+
+# ---- T4/T5: golden closed loops -----------------------------------------------------------------------
+def test_closed_loop_ms_vs_1exemplo(mv):
+    g = common.golden("unicycle_ms_1exemplo.csv")
+    solver = _solver(mv, problems.unicycle_multiple_shooting())
+    lbx, ubx = problems.unicycle_bounds(solver.spec)
+    for mode, tol_u in ((S.WARM_REFERENCE, 1e-9), (S.WARM_SHIFT, 1e-5), (S.WARM_COLD, 1e-5)):
+        r = solver.closed_loop([0, 0, 0], [10, 10, 0], None, lbx, ubx, n_steps=100, warm_mode=mode, stop_radius=0.1)
+        assert r["steps"][0] == 84 and r["status"][0] == 0        # the scripts' hard-coded reshape((85,2))
+        assert np.abs(r["controls"][0, :84] - g[:84, 3:5]).max() <= tol_u
+        assert np.abs(r["states"][0, :84] - g[1:, 0:3]).max() <= 1e-4
+    ro = O.closed_loop(solver.spec, [0, 0, 0], [10, 10, 0], None, lbx, ubx, 100, S.WARM_REFERENCE, 0.1)
+    r = solver.closed_loop([0, 0, 0], [10, 10, 0], None, lbx, ubx, n_steps=100, warm_mode=S.WARM_REFERENCE, stop_radius=0.1)
+    assert abs(int(r["iters"][0]) - int(ro["iters"][0])) <= 2
+
+
+def test_closed_loop_ss_vs_2exemplo_and_ssv1_84_steps(mv):
+    g = common.golden("unicycle_ss_2exemplo.csv")
+    solver = _solver(mv, problems.unicycle_single_shooting_rk4())
+    lbx, ubx = problems.unicycle_bounds(solver.spec)
+    r = solver.closed_loop([0, 0, 0], [10, 10, 0], None, lbx, ubx, n_steps=100, warm_mode=S.WARM_REFERENCE, stop_radius=0.1)
+    assert r["steps"][0] == 84
+    assert np.abs(r["controls"][0, :84] - g[:84, 3:5]).max() <= 1e-5
+    assert np.abs(r["states"][0, :84] - g[1:, 0:3]).max() <= 1e-4
+    eu = _solver(mv, problems.unicycle_single_shooting_euler())
+    r = eu.closed_loop([0, 0, 0], [10, 10, 0], None, lbx, ubx, n_steps=100, warm_mode=S.WARM_REFERENCE, stop_radius=0.1)
+    assert r["steps"][0] == 84
+    assert abs(np.linalg.norm(r["states"][0, 84] - [10, 10, 0]) - 0.0868) < 1e-3
+
+
+def test_closed_loop_mpctools_unicycle_vs_3exemplo(mv):
+    g = common.golden("unicycle_mpctools_3exemplo.csv")
+    solver = _solver(mv, problems.unicycle_tracking(N=10, T=0.2, M=1, Q=(1, 5, 0.1), R=(1, 1)))
+    lbx, ubx = problems.unicycle_bounds(solver.spec)
+    nst = 87
+    ptraj = np.tile([10, 10, 0, 0, 0.0], (1, nst + 10, 1))
+    r = solver.closed_loop([0, 0, 0], None, ptraj, lbx, ubx, n_steps=nst, warm_mode=S.WARM_COLD)
+    assert np.abs(r["controls"][0, :nst] - g[:nst, 3:5]).max() <= 1e-5
+
+
+@pytest.mark.parametrize("layout", [S.LAYOUT_THREAD, S.LAYOUT_WARP])
+def test_closed_loop_pendulum_vs_golden(mv, layout):
+    g = common.golden("pendulum_invertpend.csv")
+    sp0, lbx, ubx, pglob, _, _ = common.pendulum_setup(N=50, ntu=5)
+    solver = _solver(mv, {"spec": sp0}, layout=layout)
+    nst = 1000
+    ptraj = np.tile([10, 0, 0, 0, 0.0], (1, nst + 50, 1))
+    r = solver.closed_loop([0, 0, 0, 0, 0], pglob, ptraj, lbx, ubx, n_steps=nst, warm_mode=S.WARM_REFERENCE)
+    assert r["status"][0] == 0
+    assert abs(r["controls"][0, 0, 0] - (-60.84425718936204)) <= 1e-5
+    assert np.abs(r["controls"][0, :nst, 0] - g[:nst, 4]).max() <= 1e-5
+    assert np.abs(r["states"][0, :nst + 1, :4] - g[:nst + 1, :4]).max() <= 1e-4
+
+
+def test_closed_loop_batch_vs_oracle(mv):
+    solver = _solver(mv, problems.unicycle_multiple_shooting())
+    lbx, ubx = problems.unicycle_bounds(solver.spec)
+    x0s, _ = common.unicycle_batch(64, seed=9)
+    tgt = np.tile([10, 10, 0.0], (64, 1))
+    r = solver.closed_loop(x0s, tgt, None, lbx, ubx, n_steps=30, warm_mode=S.WARM_SHIFT, stop_radius=0.1)
+    ro = O.closed_loop(solver.spec, x0s, tgt, None, lbx, ubx, 30, S.WARM_SHIFT, 0.1)
+    assert np.array_equal(r["steps"], ro["steps"])
+    assert np.abs(r["controls"] - ro["controls"]).max() <= 1e-5
+    assert np.abs(r["states"] - ro["states"]).max() <= 1e-4
+
+
+# ---- full-size properties (BASELINE config 2: B = 65,536) ---------------------------------------------
+def test_full_size_properties_c2(mv):
+    import torch
+    solver = _solver(mv, problems.unicycle_multiple_shooting())
+    sp = solver.spec
+    B = 65536
+    x0s, p = common.unicycle_batch(B, seed=20261)
+    lbx, ubx = problems.unicycle_bounds(sp, x_box=20.0)
+    w0 = problems.cold_start(sp, x0s)
+    sol = solver(x0=torch.as_tensor(w0).cuda(), lbx=lbx, ubx=ubx, p=torch.as_tensor(p).cuda())
+    st = solver.stats()
+    assert st["success"]
+    x = sol["x"].cpu().numpy()
+    g = sol["g"].cpu().numpy()
+    f = sol["f"].cpu().numpy()
+    # feasibility of every defect row, bounds honoured exactly, x0 pinned
+    assert np.abs(g).max() <= 1e-8
+    assert np.all(x >= lbx - 0.0) and np.all(x <= ubx + 0.0)
+    assert np.abs(x[:, :3] - x0s).max() <= 1e-8
+    # re-rolling the returned controls reproduces the returned states and the returned cost
+    U = x[:, :50].reshape(B, 10, 5)[:, :, 3:5].reshape(B, 20)
+    X, q = solver.rollout(p, U)
+    Xs = np.concatenate([x[:, :50].reshape(B, 10, 5)[:, :, :3], x[:, None, 50:53]], 1)
+    assert np.abs(X - Xs).max() <= 1e-7
+    assert np.abs(q - f).max() <= 1e-6 * np.abs(f).max()
+    # idempotence: re-solving from the solution converges immediately to the same point
+    sol2 = solver(x0=sol["x"], lbx=lbx, ubx=ubx, p=torch.as_tensor(p).cuda())
+    assert np.abs(sol2["f"].cpu().numpy() - f).max() <= 1e-6 * np.abs(f).max()
+    # a sample of the batch against the oracle
+    idx = np.random.default_rng(0).choice(B, 512, replace=False)
+    ref = O.solve(sp, w0[idx], lbx, ubx, p[idx], nthreads=NCPU)
+    assert np.abs(x[idx] - ref["x"]).max() <= 1e-5
+    assert np.abs(f[idx] - ref["f"]).max() <= 1e-6 * np.abs(ref["f"]).max()
+
+
+def test_empty_and_ragged_batches(mv):
+    solver = _solver(mv, problems.unicycle_multiple_shooting())
+    sp = solver.spec
+    lbx, ubx = problems.unicycle_bounds(sp)
+    for B in (1, 31, 33, 129):
+        x0s, p = common.unicycle_batch(B, seed=B)
+        sol = solver(x0=problems.cold_start(sp, x0s), lbx=lbx, ubx=ubx, p=p)
+        ref = O.solve(sp, problems.cold_start(sp, x0s), lbx, ubx, p)
+        assert np.abs(np.atleast_2d(sol["x"]) - ref["x"]).max() <= 1e-6
+    sol = solver(x0=np.zeros((0, 53)), lbx=lbx, ubx=ubx, p=np.zeros((0, 6)))
+    assert sol["x"].shape == (0, 53)
+    with pytest.raises(NotImplementedError):
+        solver(x0=np.zeros(53), lbx=lbx, ubx=ubx, lbg=-1.0, ubg=1.0, p=[0, 0, 0, 10, 10, 0])
+    with pytest.raises(ValueError):
+        solver(x0=np.zeros(52), lbx=lbx, ubx=ubx, p=[0, 0, 0, 10, 10, 0])
+
+
+def test_max_iter_reported_not_raised(mv):
+    solver = mv.nlpsol("solver", "ipopt", problems.unicycle_multiple_shooting(), {"ipopt": {"max_iter": 3}})
+    lbx, ubx = problems.unicycle_bounds(solver.spec)
+    solver(x0=np.zeros(53), lbx=lbx, ubx=ubx, p=[0, 0, 0, 10, 10, 0])
+    assert solver.stats()["return_status"] == "Maximum_Iterations_Exceeded"
+    assert solver.stats()["iter_count"] == 3
+
+
+def test_fp64_peak_microbenchmark(mv):
+    t, ms = mv.fp64_peak()
+    assert 5.0 < t < 100.0, t

@@ -1,0 +1,94 @@
+"""The device headers (hand-derived sweeps + Riccati interior point) compiled as plain C++ with
+one lane per problem, against the oracle (generic AD + condensed Cholesky).  This is a
+development harness for a container without a GPU — the product never runs on the CPU."""
+import math
+
+import numpy as np
+import pytest
+
+from mpc_verde_b200 import problems
+from mpc_verde_b200 import spec as S
+from oracle import mpc_oracle as O
+from tests import common
+from tests.hostsim import hostsim as H
+
+MODELS = [
+    ("quad", lambda: S.unicycle_multiple_shooting()),
+    ("euler", lambda: S.unicycle_single_shooting_euler()),
+    ("node", lambda: S.unicycle_tracking(M=1)),
+    ("node_m3", lambda: S.unicycle_tracking(M=3)),
+    ("lin3", lambda: S.linear_tracking(3, 5, (10, 1, 0.5, 0), 0.01)),
+    ("lin4", lambda: S.linear_tracking(4, 5, (1, 2, 3, 4), 1.0)),
+    ("lin4du", lambda: S.linear_tracking(4, 5, (1.44, 0, 1, 0), 0.0, R1=1e-4)),
+    ("lin3du", lambda: S.linear_tracking(3, 5, (10, 1, 0, 0), 0.01, R1=0.5)),
+]
+
+
+@pytest.mark.parametrize("name,mk", MODELS)
+def test_hand_derivatives_vs_ad(name, mk):
+    sp = mk()
+    rng = np.random.default_rng(1)
+    B = 64
+    z = rng.normal(size=(B, sp.nx + sp.nu)) * 2
+    ps = rng.normal(size=(B, max(sp.npg + sp.nps, 1)))
+    lam = rng.normal(size=(B, sp.nx)) * 3
+    a, b = O.stage_derivs(sp, z, ps, lam), H.stage_derivs(sp, z, ps, lam)
+    for k in a:
+        assert np.abs(a[k] - b[k]).max() <= 1e-13 * (1 + np.abs(a[k]).max()), k
+
+
+def test_riccati_ipm_equals_condensed_ipm_on_random_batch():
+    sp = S.unicycle_multiple_shooting()
+    x0s, p = common.unicycle_batch(200)
+    lbx, ubx = problems.unicycle_bounds(sp, x_box=20.0)
+    w0 = problems.cold_start(sp, x0s)
+    a, b = O.solve(sp, w0, lbx, ubx, p), H.solve(sp, w0, lbx, ubx, p)
+    assert np.all(a["status"] == 0) and np.all(b["status"] == 0)
+    assert np.mean(a["iters"] == b["iters"]) >= 0.99
+    assert np.abs(a["x"] - b["x"]).max() <= 1e-9
+    assert np.abs(a["f"] - b["f"]).max() <= 1e-9 * np.abs(a["f"]).max()
+
+
+def test_zero_guess_far_from_target_exercises_backtracking_and_soc():
+    sp = S.unicycle_multiple_shooting()
+    x0s, p = common.unicycle_batch(100, seed=77)
+    lbx, ubx = problems.unicycle_bounds(sp)
+    a = O.solve(sp, None, lbx, ubx, p, want_stats=True)          # all-zeros guess (the script's w0 = 0)
+    b = H.solve(sp, None, lbx, ubx, p)
+    assert a["stats"][:, 1].sum() > 0                              # backtracks happened
+    ok = (a["status"] == 0) & (b["status"] == 0)
+    assert ok.mean() > 0.9
+    assert np.array_equal(a["status"], b["status"])
+    same = ok & (a["iters"] == b["iters"])
+    assert same.mean() > 0.95
+    assert np.abs(a["x"][same] - b["x"][same]).max() <= 1e-8
+
+
+@pytest.mark.parametrize("mode", [S.WARM_REFERENCE, S.WARM_SHIFT, S.WARM_COLD])
+def test_closed_loops_match_oracle_and_golden(mode):
+    g = common.golden("unicycle_ms_1exemplo.csv")
+    sp = S.unicycle_multiple_shooting()
+    lbx, ubx = problems.unicycle_bounds(sp)
+    a = O.closed_loop(sp, [0, 0, 0], [10, 10, 0], None, lbx, ubx, 100, mode, 0.1)
+    b = H.closed_loop(sp, [0, 0, 0], [10, 10, 0], None, lbx, ubx, 100, mode, 0.1)
+    assert a["steps"][0] == b["steps"][0] == 84
+    assert a["iters"][0] == b["iters"][0]
+    assert np.abs(a["controls"] - b["controls"]).max() <= 1e-10
+    assert np.abs(b["controls"][0, :84] - g[:84, 3:5]).max() <= 1e-5
+    for spx in (S.unicycle_single_shooting_rk4(), S.unicycle_single_shooting_euler()):
+        lb2, ub2 = problems.unicycle_bounds(spx)
+        a = O.closed_loop(spx, [0, 0, 0], [10, 10, 0], None, lb2, ub2, 100, mode, 0.1)
+        b = H.closed_loop(spx, [0, 0, 0], [10, 10, 0], None, lb2, ub2, 100, mode, 0.1)
+        assert a["steps"][0] == b["steps"][0] == 84
+        assert np.abs(a["controls"] - b["controls"]).max() <= 1e-9
+
+
+def test_pendulum_move_blocking_closed_loop():
+    g = common.golden("pendulum_invertpend.csv")
+    sp, lbx, ubx, pglob, _, _ = common.pendulum_setup(N=50, ntu=5)
+    nst = 200
+    ptraj = np.tile([10, 0, 0, 0, 0.0], (1, nst + 50, 1))
+    b = H.closed_loop(sp, [0, 0, 0, 0, 0], pglob, ptraj, lbx, ubx, nst, S.WARM_REFERENCE, 0.0)
+    assert b["status"][0] == 0
+    assert np.abs(b["controls"][0, :nst, 0] - g[:nst, 4]).max() <= 1e-5
+    assert np.abs(b["states"][0, :nst + 1, :4] - g[:nst + 1, :4]).max() <= 1e-4
