@@ -134,7 +134,10 @@ class NlpSolver:
                     "+-inf for single-shooting rows)" % nm)
 
     # -- the solve -------------------------------------------------------------------------------
-    def __call__(self, x0=None, lbx=None, ubx=None, lbg=None, ubg=None, p=None, lam_x0=None, lam_g0=None):
+    def __call__(self, x0=None, lbx=None, ubx=None, lbg=None, ubg=None, p=None, lam_x0=None, lam_g0=None,
+                 outputs=("x", "f", "g", "lam_g", "lam_x")):
+        """`outputs` selects which entries of the result dict are produced ('x' and 'f' always are;
+        the scripts read only sol['x']); skipping the rest saves their device->host copies."""
         if p is None:
             raise ValueError("p is required")
         self._check_g_bounds(lbg, ubg)
@@ -168,9 +171,12 @@ class NlpSolver:
                 status = torch.empty((B,), dtype=torch.int32, device=dev)
                 iters = torch.empty((B,), dtype=torch.int32, device=dev)
                 stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+                for k in ("g", "lam_g", "lam_x"):
+                    if k not in outputs:
+                        del out[k]
                 rc = lib.mpcv_solve(h, _ptr(x0d), _ptr(lb), _ptr(ub), _ptr(pt), _ptr(out["x"]), _ptr(out["f"]),
-                                    _ptr(out["g"]), _ptr(out["lam_g"]), _ptr(out["lam_x"]), _ptr(status), _ptr(iters),
-                                    C.c_int64(B), stream)
+                                    _ptr(out.get("g")), _ptr(out.get("lam_g")), _ptr(out.get("lam_x")), _ptr(status),
+                                    _ptr(iters), C.c_int64(B), stream)
                 _lib.check(rc, "mpcv_solve")
         else:
             # host buffers: one C-ABI call does H2D (pinned staging), solve, D2H
@@ -178,14 +184,20 @@ class NlpSolver:
             x0h = None if x0t is None else np.ascontiguousarray(x0t.numpy())
             lb = np.ascontiguousarray(self._vec(lbx, n, -math.inf, "lbx", "cpu").numpy())
             ub = np.ascontiguousarray(self._vec(ubx, n, math.inf, "ubx", "cpu").numpy())
-            out = {"x": np.empty((B, n)), "f": np.empty((B,)), "g": np.empty((B, ng)), "lam_g": np.empty((B, ng)),
-                   "lam_x": np.empty((B, n))}
+            out = {"x": np.empty((B, n)), "f": np.empty((B,))}
+            if "g" in outputs:
+                out["g"] = np.empty((B, ng))
+            if "lam_g" in outputs:
+                out["lam_g"] = np.empty((B, ng))
+            if "lam_x" in outputs:
+                out["lam_x"] = np.empty((B, n))
             status = np.empty((B,), np.int32)
             iters = np.empty((B,), np.int32)
             hp = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
             with torch.cuda.device(self.device):
-                rc = lib.mpcv_solve_host(h, hp(x0h), hp(lb), hp(ub), hp(pt), hp(out["x"]), hp(out["f"]), hp(out["g"]),
-                                         hp(out["lam_g"]), hp(out["lam_x"]), hp(status), hp(iters), C.c_int64(B))
+                rc = lib.mpcv_solve_host(h, hp(x0h), hp(lb), hp(ub), hp(pt), hp(out["x"]), hp(out["f"]),
+                                         hp(out.get("g")), hp(out.get("lam_g")), hp(out.get("lam_x")), hp(status),
+                                         hp(iters), C.c_int64(B))
             _lib.check(rc, "mpcv_solve_host")
         self._last = (status, iters)
         if unb:
