@@ -203,7 +203,7 @@ def main():
         sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     evk = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    launches0 = solver.launch_count()
+    launches0 = solver.kernel_count()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -218,7 +218,7 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    launches = solver.launch_count() - launches0
+    launches = solver.kernel_count() - launches0
     t_ms = sum(a.elapsed_time(b) for a, b in ev)
     tk_ms = sum(a.elapsed_time(b) for a, b in evk)
     if rank == 0:
@@ -293,7 +293,7 @@ def main():
         "config": {"workload": "C2 unicycle multiple shooting N=10 T=0.2 RK4(M=4)+quadrature, cold start, "
                                "x,y in [-20,20], v in [-1,1], w in [-pi/4,pi/4]",
                    "batch_per_gpu": B, "global_batch": world * B, "seed": SEED, "l2": "flushed between steps (256 MB write)",
-                   "layout": {0: "auto", 1: "thread-per-problem", 2: "warp-per-problem"}[args.layout],
+                   "layout": {0: "auto (phase kernels)", 1: "thread-per-problem", 2: "warp-per-problem", 3: "phase kernels"}[args.layout],
                    "parallelism": "problem-index sharding x%d, NCCL gather of results + stats" % world},
         "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps},

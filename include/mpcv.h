@@ -110,7 +110,11 @@ enum {
 enum {
   MPCV_LAYOUT_AUTO = 0,
   MPCV_LAYOUT_THREAD = 1,   /* one problem per thread, SoA workspace in HBM/L2 */
-  MPCV_LAYOUT_WARP = 2      /* one warp per problem, stage-parallel, shared-memory workspace */
+  MPCV_LAYOUT_WARP = 2,     /* one warp per problem, stage-parallel, shared-memory workspace */
+  MPCV_LAYOUT_PHASED = 3    /* batch-synchronous phase kernels over the thread layout's workspace: one
+                               thread per (problem, interval) for the derivative / trial sweeps, one
+                               thread per problem for the Riccati recursion, active-list compaction,
+                               one CUDA graph (conditional WHILE) per solve; multiple shooting only */
 };
 
 typedef struct mpcv_spec {
@@ -198,8 +202,14 @@ int mpcv_fp64_peak(double* tflops, double* ms, void* stream);
    difference in nanoseconds (the "p50 solve us" of BASELINE.json). NULL switches it off. */
 int mpcv_set_latency_buffer(mpcv_handle* h, long long* dev_ns);
 
-/* number of kernel launches issued through this handle since creation */
+/* number of kernel launches issued through this handle since creation (for the phased layout the
+   iteration sweeps run inside a CUDA graph: 9 kernel nodes per sweep, see mpcv_phase_sweeps) */
 int64_t mpcv_launch_count(const mpcv_handle* h);
+
+/* phased layout (synchronises `stream`): interior-point sweeps executed by the last mpcv_solve, and the
+   number of kernels run through this handle since creation INCLUDING the 9 kernel nodes of every
+   graph-driven sweep (which mpcv_launch_count cannot see from the host).  Either out may be NULL. */
+int mpcv_phase_sweeps(mpcv_handle* h, int32_t* sweeps, int64_t* kernel_nodes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -27,6 +27,19 @@ static const mpcv_model_vtable* vtable_of(int model) {
   }
 }
 
+const mpcv_phase_vtable* mpcv_phase_vtable_of(int model) {
+  switch (model) {
+    case 0: return &mpcv_phase_vtable_0;
+    case 1: return &mpcv_phase_vtable_1;
+    case 2: return &mpcv_phase_vtable_2;
+    case 3: return &mpcv_phase_vtable_3;
+    case 4: return &mpcv_phase_vtable_4;
+    case 5: return &mpcv_phase_vtable_5;
+    case 6: return &mpcv_phase_vtable_6;
+    default: return nullptr;
+  }
+}
+
 // FP64 FMA peak: 8 independent register-resident DFMA chains per thread
 __global__ void fp64_peak_kernel(double* out, int iters) {
   double a0 = threadIdx.x * 1e-3, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
@@ -93,8 +106,7 @@ mpcv_handle* mpcv_create(const mpcv_spec* s) {
   h->sm_count = prop.multiProcessorCount;
   h->max_smem_optin = prop.sharedMemPerBlockOptin;
   h->layout = s->layout;
-  if (h->layout == MPCV_LAYOUT_AUTO)
-    h->layout = (!h->single && s->N >= 32) ? MPCV_LAYOUT_WARP : MPCV_LAYOUT_THREAD;
+  if (h->layout == MPCV_LAYOUT_AUTO) h->layout = h->single ? MPCV_LAYOUT_THREAD : MPCV_LAYOUT_PHASED;
   if (h->single) h->layout = MPCV_LAYOUT_THREAD;
   if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
     mpcv_set_error(-EIO, "cudaStreamCreate"); delete h; return nullptr;
@@ -104,6 +116,7 @@ mpcv_handle* mpcv_create(const mpcv_spec* s) {
 
 void mpcv_destroy(mpcv_handle* h) {
   if (!h) return;
+  if (h->phase) mpcv_phase_vtable_of(h->spec.model)->release(h->phase);
   if (h->slab) cudaFree(h->slab);
   if (h->hpin) cudaFreeHost(h->hpin);
   if (h->dstage) cudaFree(h->dstage);
@@ -112,6 +125,16 @@ void mpcv_destroy(mpcv_handle* h) {
 }
 
 int64_t mpcv_launch_count(const mpcv_handle* h) { return h ? h->launches : 0; }
+
+int mpcv_phase_sweeps(mpcv_handle* h, int32_t* sweeps, int64_t* kernel_nodes, void* stream) {
+  if (!h) return mpcv_set_error(-EINVAL, "mpcv_phase_sweeps: null argument");
+  int n = 0, cum = 0;
+  if (int rc = mpcv_phase_vtable_of(h->spec.model)->sweeps(h, (cudaStream_t)stream, &n, &cum)) return rc;
+  if (sweeps) *sweeps = n;
+  // launches issued from the host + 9 kernel nodes per graph-driven sweep
+  if (kernel_nodes) *kernel_nodes = h->launches + (h->phase_graph_launches > 0 ? 9 * (int64_t)cum : 0);
+  return 0;
+}
 
 int mpcv_set_latency_buffer(mpcv_handle* h, long long* dev_ns) {
   if (!h) return mpcv_set_error(-EINVAL, "null handle");

@@ -39,6 +39,8 @@ struct mpcv_handle {
   cudaStream_t own_stream = nullptr;
   long long* latency_ns = nullptr;   // optional device buffer [B]
   int64_t launches = 0;
+  struct mpcv_phase_state* phase = nullptr;   // phase-kernel pipeline resources (mpcv_phase_inst.cu)
+  int64_t phase_graph_launches = 0;
 };
 
 // per-model entry points (defined once per model in mpcv_inst.cu, -DMPCV_INST_MODEL=<id>)
@@ -51,6 +53,15 @@ struct mpcv_model_vtable {
   int (*derivs)(mpcv_handle*, const double*, const double*, const double*, double*, double*, double*, double*,
                 double*, double*, long, cudaStream_t);
 };
-#define MPCV_DECLARE_MODEL(id) extern const mpcv_model_vtable mpcv_model_vtable_##id;
+// phase-kernel pipeline of one model (mpcv_phase_inst.cu, -DMPCV_INST_MODEL=<id>)
+struct mpcv_phase_vtable {
+  int (*solve)(mpcv_handle*, const mpcv::SolveIO&, long, cudaStream_t);
+  void (*release)(struct mpcv_phase_state*);
+  int (*sweeps)(mpcv_handle*, cudaStream_t, int*, int*);
+};
+const mpcv_phase_vtable* mpcv_phase_vtable_of(int model);
+#define MPCV_DECLARE_MODEL(id) \
+  extern const mpcv_model_vtable mpcv_model_vtable_##id; \
+  extern const mpcv_phase_vtable mpcv_phase_vtable_##id;
 MPCV_DECLARE_MODEL(0) MPCV_DECLARE_MODEL(1) MPCV_DECLARE_MODEL(2) MPCV_DECLARE_MODEL(3)
 MPCV_DECLARE_MODEL(4) MPCV_DECLARE_MODEL(5) MPCV_DECLARE_MODEL(6)

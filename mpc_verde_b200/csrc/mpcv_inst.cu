@@ -3,7 +3,7 @@
 //
 // Two execution shapes (see mpcv_ipm.cuh):
 //   *_thread_kernel : one problem per thread.  Workspace is a structure-of-arrays slab in HBM
-//       (element i of problem b at slab[i*stride + b]) so the 32 problems of a warp read and
+//       (warp-blocked: element i of problem b at slab[(b/32)*32*total + i*32 + b%32]) so the 32 problems of a warp read and
 //       write 256-byte contiguous runs.  Used for tiny problems (nx <= 4, N <= 20-ish).
 //   *_warp_kernel   : one problem per warp, persistent grid (CTAs sized to the SM count), per-warp
 //       workspace in shared memory, stage-parallel derivative / line-search evaluation, shuffle
@@ -17,22 +17,7 @@ using namespace mpcv;
 #ifndef MPCV_INST_MODEL
 #error "compile with -DMPCV_INST_MODEL=<model id>"
 #endif
-#if MPCV_INST_MODEL == 0
-using ModelT = Unicycle<0>;
-#elif MPCV_INST_MODEL == 1
-using ModelT = Unicycle<1>;
-#elif MPCV_INST_MODEL == 2
-using ModelT = Unicycle<2>;
-#elif MPCV_INST_MODEL == 3
-using ModelT = Linear<3, false>;
-#elif MPCV_INST_MODEL == 4
-using ModelT = Linear<4, false>;
-#elif MPCV_INST_MODEL == 5
-using ModelT = Linear<4, true>;
-#elif MPCV_INST_MODEL == 6
-using ModelT = Linear<3, true>;
-#endif
-static_assert(ModelT::MODEL_ID == MPCV_INST_MODEL, "model id mismatch");
+#include "mpcv_model_select.h"
 
 // ---------------------------------------------------------------------------------------
 // TMA bulk-copy stager for shared-memory workspaces (warp layout)
@@ -102,20 +87,20 @@ __device__ __forceinline__ long long globaltimer_ns() {
 
 template <class Model, bool SINGLE>
 __global__ void __launch_bounds__(128)
-solve_thread_kernel(const Params P, const Layout L, const SolveIO io, double* slab, long stride, long B) {
+solve_thread_kernel(const Params P, const Layout L, const SolveIO io, double* slab, long B) {
   const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const long long t0 = io.ns ? globaltimer_ns() : 0;
-  solve_problem<Model, SINGLE, 1, WsStrided>(P, L, WsStrided{slab + b, stride}, Grp<1>(0), io, b);
+  solve_problem<Model, SINGLE, 1, WsStrided>(P, L, WsStrided::of(slab, L.total, b), Grp<1>(0), io, b);
   if (io.ns) io.ns[b] = globaltimer_ns() - t0;
 }
 
 template <class Model, bool SINGLE>
 __global__ void __launch_bounds__(128)
-loop_thread_kernel(const Params P, const Layout L, const LoopIO io, double* slab, long stride, long B) {
+loop_thread_kernel(const Params P, const Layout L, const LoopIO io, double* slab, long B) {
   const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  closed_loop_problem<Model, SINGLE, 1, WsStrided>(P, L, WsStrided{slab + b, stride}, Grp<1>(0), io, b);
+  closed_loop_problem<Model, SINGLE, 1, WsStrided>(P, L, WsStrided::of(slab, L.total, b), Grp<1>(0), io, b);
 }
 
 constexpr int kWarpKernelMaxWarps = 8;
@@ -270,6 +255,7 @@ static int warp_config(const mpcv_handle* h, int* wpb, size_t* smem) {
 template <class Model>
 static int launch_solve(mpcv_handle* h, const SolveIO& io, long B, cudaStream_t st) {
   if (B <= 0) return 0;
+  if (h->layout == MPCV_LAYOUT_PHASED && !h->single) return mpcv_phase_vtable_of(Model::MODEL_ID)->solve(h, io, B, st);
   if (h->layout == MPCV_LAYOUT_WARP && !h->single) {
     int wpb; size_t smem;
     if (int rc = warp_config(h, &wpb, &smem)) return rc;
@@ -286,8 +272,8 @@ static int launch_solve(mpcv_handle* h, const SolveIO& io, long B, cudaStream_t 
     if (int rc = ensure_slab(h, B)) return rc;
     const int threads = 128;
     const unsigned grid = (unsigned)((B + threads - 1) / threads);
-    if (h->single) solve_thread_kernel<Model, true><<<grid, threads, 0, st>>>(h->P, h->L, io, h->slab, h->slab_stride, B);
-    else solve_thread_kernel<Model, false><<<grid, threads, 0, st>>>(h->P, h->L, io, h->slab, h->slab_stride, B);
+    if (h->single) solve_thread_kernel<Model, true><<<grid, threads, 0, st>>>(h->P, h->L, io, h->slab, B);
+    else solve_thread_kernel<Model, false><<<grid, threads, 0, st>>>(h->P, h->L, io, h->slab, B);
   }
   h->launches++;
   CUDA_OK(cudaGetLastError());
@@ -297,7 +283,9 @@ static int launch_solve(mpcv_handle* h, const SolveIO& io, long B, cudaStream_t 
 template <class Model>
 static int launch_loop(mpcv_handle* h, const LoopIO& io, long B, cudaStream_t st) {
   if (B <= 0) return 0;
-  if (h->layout == MPCV_LAYOUT_WARP && !h->single) {
+  // the closed loop runs as one kernel per call: warp layout for long horizons, thread layout otherwise
+  const bool warp = h->layout == MPCV_LAYOUT_WARP || (h->layout == MPCV_LAYOUT_PHASED && h->spec.N >= 32);
+  if (warp && !h->single) {
     int wpb; size_t smem;
     if (int rc = warp_config(h, &wpb, &smem)) return rc;
     auto kern = loop_warp_kernel<Model>;
@@ -313,8 +301,8 @@ static int launch_loop(mpcv_handle* h, const LoopIO& io, long B, cudaStream_t st
     if (int rc = ensure_slab(h, B)) return rc;
     const int threads = 128;
     const unsigned grid = (unsigned)((B + threads - 1) / threads);
-    if (h->single) loop_thread_kernel<Model, true><<<grid, threads, 0, st>>>(h->P, h->L, io, h->slab, h->slab_stride, B);
-    else loop_thread_kernel<Model, false><<<grid, threads, 0, st>>>(h->P, h->L, io, h->slab, h->slab_stride, B);
+    if (h->single) loop_thread_kernel<Model, true><<<grid, threads, 0, st>>>(h->P, h->L, io, h->slab, B);
+    else loop_thread_kernel<Model, false><<<grid, threads, 0, st>>>(h->P, h->L, io, h->slab, B);
   }
   h->launches++;
   CUDA_OK(cudaGetLastError());

@@ -17,8 +17,8 @@
 //     Cholesky of H + Sigma + delta_w I.
 //
 // Execution shape: a group of LANES threads owns one problem.  LANES = 1 is the
-// thread-per-problem layout (workspace: structure-of-arrays in HBM, element i of problem b
-// at ws[i*stride + b], so a warp's accesses coalesce).  LANES = 32 is the warp-per-problem
+// thread-per-problem layout (workspace: warp-blocked structure-of-arrays in HBM, see WsStrided,
+// so a warp's accesses coalesce).  LANES = 32 is the warp-per-problem
 // layout (workspace in shared memory, stage-parallel derivative / trial evaluation, shuffle
 // reductions for the merit function, step norms and convergence tests; the sequential
 // Riccati sweeps run on lane 0).
@@ -69,11 +69,20 @@ struct Grp {
 #endif
 };
 
-// strided workspace view: element i lives at base[i*stride]
+// Warp-blocked structure of arrays in HBM (thread layout and phase kernels): the 32 problems of
+// block (b >> 5) keep element i in 32 consecutive doubles, so a warp reads or writes one 256-byte run
+// per element AND element offsets are compile-time immediates (i * 256 bytes) off one per-thread
+// base pointer — no index arithmetic per access.
 struct WsStrided {
   double* base;
-  long stride;
-  MPCV_HD double& operator[](int i) const { return base[(long)i * stride]; }
+  MPCV_HD double& operator[](int i) const { return base[(long)i * 32]; }
+  MPCV_HD static WsStrided of(double* slab, int total, long b) {
+    double* p = slab + (b >> 5) * ((long)total * 32) + (b & 31);
+#if defined(__CUDA_ARCH__)
+    __builtin_assume(__isGlobal(p));   // plain ld.global / st.global instead of generic accesses
+#endif
+    return WsStrided{p};
+  }
 };
 // contiguous workspace view (shared memory / host harness)
 struct WsDense {
@@ -92,8 +101,17 @@ struct WsView {
 // ---------------------------------------------------------------------------------------
 struct Layout {
   int n, m, N;
-  int w, lam, zl, zu, d, lamp, grad, c, ct, ab, hw, ric, pp, par, xs, hred, gam, tmp, total;
+  int w, lam, zl, zu, d, lamp, grad, c, ct, ab, hw, ric, pp, par, xs, hred, gam, tmp;
+  int sig, rb;   // Sigma_i and barrier-gradient r_i of the current iterate (filled once per iteration)
+  int qs;        // per-stage interval costs (stage-parallel kernels hand them to the per-problem reduction)
+  int st;        // persistent scalar state of the solve (phase-kernel pipeline), kStateSlots doubles
+  int total;
 };
+
+// Relaxed bounds of one variable, precomputed once per kernel (the bounds are shared by the batch).
+struct BndEntry { double lo, hi; int flags, pad; };   // flags: 1 = lower, 2 = upper, 4 = fixed
+constexpr int kStateSlots = 32;
+constexpr int kRunning = 1000;    // internal "not finished" status
 
 template <class Model, bool SINGLE>
 MPCV_HD Layout make_layout(int N) {
@@ -112,6 +130,10 @@ MPCV_HD Layout make_layout(int N) {
   L.ab = o; o += N * (NX * NX + NX * NU);
   L.hw = o; o += N * (NZ * (NZ + 1) / 2);
   L.par = o; o += NX + Model::NPG + N * Model::NPS + 2;   // +2: alignment slack for bulk-staged stage params
+  L.sig = o; o += L.n;
+  L.rb = o; o += L.n;
+  L.qs = o; o += N;
+  L.st = o; o += kStateSlots;
   L.lamp = L.c = L.ct = L.ric = L.pp = L.xs = L.hred = L.gam = L.tmp = 0;
   if (SINGLE) {
     L.xs = o; o += NX * (N + 1);
@@ -153,15 +175,43 @@ struct Ipm {
   Grp<LANES> g;
   const double* lbx;   // [n] original bounds, shared by the batch
   const double* ubx;
+  const BndEntry* btab;   // optional precomputed relaxed bounds (shared memory); null = compute on the fly
   const int N;
 
   int ps_base;         // offset of the stage parameters (shifted by 0/1 to match the source's 16-byte phase)
+  // persistent scalar state of one solve (saved to / restored from ws[L.st..] between phase kernels)
   double df, mu, tau, f_curr;
+  double theta_max, theta_min, delta_w_last;
   double fil_phi[FILTER_MAX], fil_th[FILTER_MAX];
-  int nfil;
+  int nfil, iter;
+  // search direction -> line search hand-over
+  double ls_alpha_max, ls_theta, ls_gBD, ls_phi;
 
-  MPCV_D Ipm(const Params& p, const Layout& l, WS w, Grp<LANES> grp, const double* lb, const double* ub)
-      : P(p), L(l), ws(w), g(grp), lbx(lb), ubx(ub), N(l.N), ps_base(l.par + NX + Model::NPG), df(1.0), mu(0.1), tau(0.99), f_curr(0), nfil(0) {}
+  MPCV_D Ipm(const Params& p, const Layout& l, WS w, Grp<LANES> grp, const double* lb, const double* ub,
+             const BndEntry* tab = nullptr)
+      : P(p), L(l), ws(w), g(grp), lbx(lb), ubx(ub), btab(tab), N(l.N), ps_base(l.par + NX + Model::NPG),
+        df(1.0), mu(0.1), tau(0.99), f_curr(0), theta_max(-1.0), theta_min(-1.0), delta_w_last(0.0), nfil(0),
+        iter(0), ls_alpha_max(1.0), ls_theta(0.0), ls_gBD(0.0), ls_phi(0.0) {}
+
+  // ---- state hand-over between phase kernels ---------------------------------------------------
+  MPCV_D void save_state(int status) const {
+    const int o = L.st;
+    if (g.lane != 0) return;
+    ws[o + 0] = df; ws[o + 1] = mu; ws[o + 2] = tau; ws[o + 3] = f_curr;
+    ws[o + 4] = theta_max; ws[o + 5] = theta_min; ws[o + 6] = delta_w_last;
+    ws[o + 7] = (double)nfil; ws[o + 8] = (double)iter; ws[o + 9] = (double)status;
+    ws[o + 10] = ls_alpha_max; ws[o + 11] = ls_theta; ws[o + 12] = ls_gBD; ws[o + 13] = ls_phi;
+    for (int q = 0; q < nfil; ++q) { ws[o + 16 + q] = fil_phi[q]; ws[o + 24 + q] = fil_th[q]; }
+  }
+  MPCV_D int load_state() {
+    const int o = L.st;
+    df = ws[o + 0]; mu = ws[o + 1]; tau = ws[o + 2]; f_curr = ws[o + 3];
+    theta_max = ws[o + 4]; theta_min = ws[o + 5]; delta_w_last = ws[o + 6];
+    nfil = (int)ws[o + 7]; iter = (int)ws[o + 8];
+    ls_alpha_max = ws[o + 10]; ls_theta = ws[o + 11]; ls_gBD = ws[o + 12]; ls_phi = ws[o + 13];
+    for (int q = 0; q < nfil; ++q) { fil_phi[q] = ws[o + 16 + q]; fil_th[q] = ws[o + 24 + q]; }
+    return (int)ws[o + 9];
+  }
 
   // ---- variable indexing ------------------------------------------------------------------
   MPCV_D int ix(int k, int i) const { return k * NZ + i; }            // multiple shooting only
@@ -176,7 +226,7 @@ struct Ipm {
   }
 
   struct Bnd { double lo, hi; bool hasl, hasu, fixed; };
-  MPCV_D Bnd bnd(int i) const {
+  MPCV_D Bnd bnd_compute(int i) const {
     Bnd b;
     const double l = lbx[i], u = ubx[i];
     b.hasl = l > -kInfBound;
@@ -186,6 +236,22 @@ struct Ipm {
     b.lo = b.hasl ? l - P.bound_relax * fmax(1.0, fabs(l)) : -INFINITY;
     b.hi = b.hasu ? u + P.bound_relax * fmax(1.0, fabs(u)) : INFINITY;
     return b;
+  }
+  MPCV_D Bnd bnd(int i) const {
+    if (btab) {
+      const BndEntry e = btab[i];
+      Bnd b;
+      b.lo = e.lo; b.hi = e.hi;
+      b.hasl = (e.flags & 1) != 0; b.hasu = (e.flags & 2) != 0; b.fixed = (e.flags & 4) != 0;
+      return b;
+    }
+    return bnd_compute(i);
+  }
+  MPCV_D BndEntry bnd_entry(int i) const {
+    const Bnd b = bnd_compute(i);
+    BndEntry e;
+    e.lo = b.lo; e.hi = b.hi; e.flags = (b.hasl ? 1 : 0) | (b.hasu ? 2 : 0) | (b.fixed ? 4 : 0); e.pad = 0;
+    return e;
   }
 
   MPCV_D WsView<WS> pg() const { return WsView<WS>{ws, L.par + NX}; }
@@ -214,6 +280,47 @@ struct Ipm {
   }
 
   // ---- derivatives at the current iterate ---------------------------------------------------
+  // One shooting interval: fills ab, hw (when want_hess), grad (df * grad f) and the defect
+  // c_{k+1} of stage k; returns the interval cost q_k.  (Multiple shooting; stage-parallel.)
+  MPCV_D double der_stage(int k, bool want_hess) const {
+    double x[NX], u[NU], lamn[NX], xn[NX], A[NX * NX], B[NX * NU], q, gq[NZ], W[NW];
+    load_xu(k, L.w, 0.0, 0, x, u);
+#pragma unroll
+    for (int i = 0; i < NX; ++i) lamn[i] = ws[L.lam + (k + 1) * NX + i];
+    Model::der(P, x, u, pg(), ps(k), lamn, df, want_hess, xn, A, B, &q, gq, W);
+    if (blocked(k)) fold_blocked(A, B, gq, want_hess ? W : nullptr);
+#pragma unroll
+    for (int i = 0; i < NX * NX; ++i) ws[L.ab + k * NAB + i] = A[i];
+#pragma unroll
+    for (int i = 0; i < NX * NU; ++i) ws[L.ab + k * NAB + NX * NX + i] = B[i];
+    if (want_hess) {
+#pragma unroll
+      for (int i = 0; i < NW; ++i) ws[L.hw + k * NW + i] = W[i];
+    }
+#pragma unroll
+    for (int i = 0; i < NX; ++i) ws[L.grad + ix(k, i)] = df * gq[i];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) ws[L.grad + iu(k, i)] = df * gq[NX + i];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) ws[L.c + (k + 1) * NX + i] = xn[i] - ws[L.w + ix(k + 1, i)];
+    return q;
+  }
+  // rows that belong to no interval: c_0 = xbar - X0 (MS:125-130) and the terminal gradient
+  MPCV_D void der_terminal() const {
+#pragma unroll
+    for (int i = 0; i < NX; ++i) {
+      ws[L.c + i] = ws[L.par + i] - ws[L.w + ix(0, i)];
+      ws[L.grad + ix(N, i)] = 0.0;                         // no terminal cost in the scripts
+    }
+  }
+  // scaled objective from the per-stage costs left in ws[L.qs..] by the stage-parallel kernels
+  // (same summation order as the in-line accumulation of eval_derivatives / eval_trial)
+  MPCV_D double sum_stage_costs() const {
+    double fpart = 0.0;
+    for (int k = 0; k < N; ++k) fpart += ws[L.qs + k];
+    return df * fpart;
+  }
+
   // fills ab, hw (when want_hess), grad (df * grad f), c (MS) and f_curr (scaled objective)
   MPCV_DN void eval_derivatives(bool want_hess) {
     if (SINGLE) {
@@ -221,36 +328,8 @@ struct Ipm {
       return;
     }
     double fpart = 0.0;
-    for (int k = g.lane; k < N; k += LANES) {
-      double x[NX], u[NU], lamn[NX], xn[NX], A[NX * NX], B[NX * NU], q, gq[NZ], W[NW];
-      load_xu(k, L.w, 0.0, 0, x, u);
-#pragma unroll
-      for (int i = 0; i < NX; ++i) lamn[i] = ws[L.lam + (k + 1) * NX + i];
-      Model::der(P, x, u, pg(), ps(k), lamn, df, want_hess, xn, A, B, &q, gq, W);
-      if (blocked(k)) fold_blocked(A, B, gq, want_hess ? W : nullptr);
-      fpart += q;
-#pragma unroll
-      for (int i = 0; i < NX * NX; ++i) ws[L.ab + k * NAB + i] = A[i];
-#pragma unroll
-      for (int i = 0; i < NX * NU; ++i) ws[L.ab + k * NAB + NX * NX + i] = B[i];
-      if (want_hess) {
-#pragma unroll
-        for (int i = 0; i < NW; ++i) ws[L.hw + k * NW + i] = W[i];
-      }
-#pragma unroll
-      for (int i = 0; i < NX; ++i) ws[L.grad + ix(k, i)] = df * gq[i];
-#pragma unroll
-      for (int i = 0; i < NU; ++i) ws[L.grad + iu(k, i)] = df * gq[NX + i];
-#pragma unroll
-      for (int i = 0; i < NX; ++i) ws[L.c + (k + 1) * NX + i] = xn[i] - ws[L.w + ix(k + 1, i)];
-    }
-    if (g.lane == 0) {
-#pragma unroll
-      for (int i = 0; i < NX; ++i) {
-        ws[L.c + i] = ws[L.par + i] - ws[L.w + ix(0, i)];   // xbar - X0 (MS:125-130)
-        ws[L.grad + ix(N, i)] = 0.0;                         // no terminal cost in the scripts
-      }
-    }
+    for (int k = g.lane; k < N; k += LANES) fpart += der_stage(k, want_hess);
+    if (g.lane == 0) der_terminal();
     f_curr = df * g.sum(fpart);
     g.sync();
   }
@@ -403,6 +482,44 @@ struct Ipm {
     if (store_ct) g.sync();
   }
 
+  // Stage-parallel form of eval_trial for the phase-kernel pipeline (multiple shooting):
+  // trial_stage(k) leaves the defect of interval k in ct and its cost in qs; trial_reduce() adds the
+  // x0 rows, the barrier terms and sums in the order eval_trial accumulates.
+  MPCV_D void trial_stage(int k, double alpha, int doff) const {
+    double x[NX], u[NU], xn[NX], q;
+    load_xu(k, L.w, alpha, doff, x, u);
+    Model::val(P, x, u, pg(), ps(k), xn, &q);
+    ws[L.qs + k] = q;
+#pragma unroll
+    for (int i = 0; i < NX; ++i)
+      ws[L.ct + (k + 1) * NX + i] = xn[i] - (ws[L.w + ix(k + 1, i)] + alpha * ws[doff + ix(k + 1, i)]);
+  }
+  MPCV_D void trial_reduce(double alpha, int doff, double* f_out, double* theta_out, double* phi_out) const {
+    double thpart = 0.0, logpart = 0.0;
+    bool bad = false;
+    for (int i = NX + g.lane; i < L.m; i += LANES) thpart += fabs(ws[L.ct + i]);
+    for (int i = g.lane; i < NX; i += LANES) {
+      const double r = ws[L.par + i] - (ws[L.w + ix(0, i)] + alpha * ws[doff + ix(0, i)]);
+      thpart += fabs(r);
+      ws[L.ct + i] = r;
+    }
+    for (int i = g.lane; i < L.n; i += LANES) {
+      const Bnd b = bnd(i);
+      if (b.hasl || b.hasu) {
+        const double v = ws[L.w + i] + alpha * ws[doff + i];
+        if (b.hasl) { const double s = v - b.lo; if (!(s > 0.0)) bad = true; logpart += log(s); }
+        if (b.hasu) { const double s = b.hi - v; if (!(s > 0.0)) bad = true; logpart += log(s); }
+      }
+    }
+    const double f = sum_stage_costs();
+    const double lg = g.sum(logpart);
+    const bool anybad = g.max(bad ? 1.0 : 0.0) > 0.0;
+    *f_out = f;
+    *theta_out = g.sum(thpart);
+    *phi_out = anybad ? INFINITY : f - mu * lg;
+    g.sync();
+  }
+
   // ---- error measures (scaled as in IPOPT's E_mu) ------------------------------------------------
   struct Err { double dual, prim, cmin, cmax, sd, sc; bool any_bound; };
   MPCV_DN Err errors() const {
@@ -475,17 +592,71 @@ struct Ipm {
   MPCV_D static double Emu(const Err& e, double mu_t) { return fmax(e.dual, fmax(e.prim, compl_err(e, mu_t))); }
 
   // ---- Sigma and barrier gradient of variable i -----------------------------------------------------
-  MPCV_D void sigma_r(int i, double* sg, double* r) const {
+  // computed once per iteration (after the barrier update) and reused by the factorisation
+  // retries, the vector recursions and the merit-function slope
+  MPCV_D void sigma_r_compute(int i, double* sg, double* r) const {
     const Bnd b = bnd(i);
     double s = 0.0, ri = ws[L.grad + i];
-    if (b.hasl) { const double sl = ws[L.w + i] - b.lo; s += ws[L.zl + i] / sl; ri -= mu / sl; }
-    if (b.hasu) { const double su = b.hi - ws[L.w + i]; s += ws[L.zu + i] / su; ri += mu / su; }
+    // one reciprocal per bound serves Sigma = z / s and the barrier gradient mu / s
+    if (b.hasl) { const double inv = 1.0 / (ws[L.w + i] - b.lo); s += ws[L.zl + i] * inv; ri -= mu * inv; }
+    if (b.hasu) { const double inv = 1.0 / (b.hi - ws[L.w + i]); s += ws[L.zu + i] * inv; ri += mu * inv; }
     *sg = s; *r = ri;
   }
+  MPCV_D void prepare_barrier() const {
+    for (int i = g.lane; i < L.n; i += LANES) {
+      double sg, r;
+      sigma_r_compute(i, &sg, &r);
+      ws[L.sig + i] = sg;
+      ws[L.rb + i] = r;
+    }
+    g.sync();
+  }
+  MPCV_D void sigma_r(int i, double* sg, double* r) const { *sg = ws[L.sig + i]; *r = ws[L.rb + i]; }
 
   // ---- Riccati factorisation (multiple shooting) ------------------------------------------------------
   // identity=true replaces the Lagrangian Hessian by I and drops Sigma (least-squares multipliers).
   // Stores per stage: K (NU x NX), chol(F) packed, P_k packed; returns false on wrong inertia.
+  // L1 prefetch of a workspace element (no register cost; no-op on the host harness)
+  MPCV_D void pf(int i) const {
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(&ws[i]));
+#else
+    (void)i;
+#endif
+  }
+  // operands of one backward Riccati step, loaded as a block; the rows of stage k-1 are prefetched into L1
+  // while stage k computes (the recursion is a chain of dependent steps: without the prefetch every step
+  // starts with an exposed HBM round trip)
+  struct FacIn { double A[NX * NX], B[NX * NU], W[NW], sg[NZ]; };
+  MPCV_D void prefetch_fac(int k, bool identity) const {
+    if (LANES != 1) return;          // shared-memory workspaces have nothing to prefetch
+#pragma unroll
+    for (int i = 0; i < NAB; ++i) pf(L.ab + k * NAB + i);
+    if (!identity) {
+#pragma unroll
+      for (int i = 0; i < NW; ++i) pf(L.hw + k * NW + i);
+#pragma unroll
+      for (int i = 0; i < NZ; ++i) pf(L.sig + k * NZ + i);
+    }
+  }
+  MPCV_D void load_fac(int k, bool identity, FacIn& s) const {
+#pragma unroll
+    for (int i = 0; i < NX * NX; ++i) s.A[i] = ws[L.ab + k * NAB + i];
+#pragma unroll
+    for (int i = 0; i < NX * NU; ++i) s.B[i] = ws[L.ab + k * NAB + NX * NX + i];
+    if (identity) {
+#pragma unroll
+      for (int i = 0; i < NW; ++i) s.W[i] = 0.0;
+#pragma unroll
+      for (int i = 0; i < NZ; ++i) { s.W[tri(i, i)] = 1.0; s.sg[i] = 0.0; }
+    } else {
+#pragma unroll
+      for (int i = 0; i < NW; ++i) s.W[i] = ws[L.hw + k * NW + i];
+#pragma unroll
+      for (int i = 0; i < NZ; ++i) s.sg[i] = ws[L.sig + k * NZ + i];
+    }
+  }
+
   MPCV_DN bool riccati_factor(double dw, bool identity) {
     int ok = 1;
     if (g.lane == 0) {
@@ -499,26 +670,20 @@ struct Ipm {
         Pm[i * NX + i] = (identity ? 1.0 : 0.0) + sg + dw;
       }
       store_P(N, Pm);
+      FacIn cur;
       for (int k = N - 1; k >= 0 && ok; --k) {
+        load_fac(k, identity, cur);
+        if (k > 0) prefetch_fac(k - 1, identity);
         double A[NX * NX], B[NX * NU], W[NW];
 #pragma unroll
-        for (int i = 0; i < NX * NX; ++i) A[i] = ws[L.ab + k * NAB + i];
+        for (int i = 0; i < NX * NX; ++i) A[i] = cur.A[i];
 #pragma unroll
-        for (int i = 0; i < NX * NU; ++i) B[i] = ws[L.ab + k * NAB + NX * NX + i];
-        if (identity) {
+        for (int i = 0; i < NX * NU; ++i) B[i] = cur.B[i];
 #pragma unroll
-          for (int i = 0; i < NW; ++i) W[i] = 0.0;
+        for (int i = 0; i < NW; ++i) W[i] = cur.W[i];
+        if (!identity) {
 #pragma unroll
-          for (int i = 0; i < NZ; ++i) W[tri(i, i)] = 1.0;
-        } else {
-#pragma unroll
-          for (int i = 0; i < NW; ++i) W[i] = ws[L.hw + k * NW + i];
-#pragma unroll
-          for (int i = 0; i < NZ; ++i) {
-            double sg, r;
-            sigma_r(k * NZ + i, &sg, &r);
-            W[tri(i, i)] += sg + dw;
-          }
+          for (int i = 0; i < NZ; ++i) W[tri(i, i)] += cur.sg[i] + dw;
         }
         // PA = P A, PB = P B
         double PA[NX * NX], PB[NX * NU];
@@ -659,35 +824,116 @@ struct Ipm {
   // ---- Riccati solve: vector recursions with the stored factors ------------------------------------
   // rhs: r = barrier gradient (rmode 0) or grad - zl + zu (rmode 1, least squares);
   // residuals from offset coff (L.c, L.ct) or zero (coff < 0).  Writes d and lam+ (L.lamp).
+  // Both sweeps prefetch the next stage's rows into L1 (see prefetch_fac).
+  struct BwdIn { double P[NPX], c[NX], A[NX * NX], B[NX * NU], K[NU * NX], F[NF], ru[NU], rx[NX]; };
+  struct FwdIn { double P[NPX], p[NX], K[NU * NX], kff[NU], A[NX * NX], B[NX * NU], c[NX]; };
+  MPCV_D double rvar(int rmode, int v) const {
+    if (rmode == 1) return ws[L.grad + v] - ws[L.zl + v] + ws[L.zu + v];
+    return ws[L.rb + v];
+  }
+  MPCV_D void load_bwd(int k, int rmode, int coff, BwdIn& s) const {
+    const int ao = L.ab + k * NAB, ro = L.ric + k * NRIC;
+#pragma unroll
+    for (int i = 0; i < NPX; ++i) s.P[i] = ws[L.pp + (k + 1) * NPP + i];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) s.c[i] = (coff >= 0) ? ws[coff + (k + 1) * NX + i] : 0.0;
+#pragma unroll
+    for (int i = 0; i < NX * NX; ++i) s.A[i] = ws[ao + i];
+#pragma unroll
+    for (int i = 0; i < NX * NU; ++i) s.B[i] = ws[ao + NX * NX + i];
+#pragma unroll
+    for (int i = 0; i < NU * NX; ++i) s.K[i] = ws[ro + i];
+#pragma unroll
+    for (int i = 0; i < NF; ++i) s.F[i] = ws[ro + NU * NX + NU + i];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) s.ru[i] = rvar(rmode, iu(k, i));
+#pragma unroll
+    for (int i = 0; i < NX; ++i) s.rx[i] = rvar(rmode, ix(k, i));
+  }
+  MPCV_D void prefetch_bwd(int k, int rmode, int coff) const {
+    if (LANES != 1) return;
+#pragma unroll
+    for (int i = 0; i < NPX; ++i) pf(L.pp + (k + 1) * NPP + i);
+    if (coff >= 0) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) pf(coff + (k + 1) * NX + i);
+    }
+#pragma unroll
+    for (int i = 0; i < NAB; ++i) pf(L.ab + k * NAB + i);
+#pragma unroll
+    for (int i = 0; i < NU * NX; ++i) pf(L.ric + k * NRIC + i);
+#pragma unroll
+    for (int i = 0; i < NF; ++i) pf(L.ric + k * NRIC + NU * NX + NU + i);
+    if (rmode == 0) {
+#pragma unroll
+      for (int i = 0; i < NZ; ++i) pf(L.rb + k * NZ + i);
+    }
+  }
+  MPCV_D void prefetch_fwd(int k, int coff) const {
+    if (LANES != 1) return;
+#pragma unroll
+    for (int i = 0; i < NPP; ++i) pf(L.pp + k * NPP + i);
+    if (k == N) return;
+#pragma unroll
+    for (int i = 0; i < NU * NX + NU; ++i) pf(L.ric + k * NRIC + i);
+#pragma unroll
+    for (int i = 0; i < NAB; ++i) pf(L.ab + k * NAB + i);
+    if (coff >= 0) {
+#pragma unroll
+      for (int i = 0; i < NX; ++i) pf(coff + (k + 1) * NX + i);
+    }
+  }
+  MPCV_D void load_fwd(int k, int coff, FwdIn& s) const {
+#pragma unroll
+    for (int i = 0; i < NPX; ++i) s.P[i] = ws[L.pp + k * NPP + i];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) s.p[i] = ws[L.pp + k * NPP + NPX + i];
+    if (k == N) return;
+    const int ao = L.ab + k * NAB, ro = L.ric + k * NRIC;
+#pragma unroll
+    for (int i = 0; i < NU * NX; ++i) s.K[i] = ws[ro + i];
+#pragma unroll
+    for (int i = 0; i < NU; ++i) s.kff[i] = ws[ro + NU * NX + i];
+#pragma unroll
+    for (int i = 0; i < NX * NX; ++i) s.A[i] = ws[ao + i];
+#pragma unroll
+    for (int i = 0; i < NX * NU; ++i) s.B[i] = ws[ao + NX * NX + i];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) s.c[i] = (coff >= 0) ? ws[coff + (k + 1) * NX + i] : 0.0;
+  }
+
   MPCV_DN void riccati_solve(int rmode, int coff) const {
     if (g.lane == 0) {
       double pv[NX];   // p_{k+1}
-      auto rvar = [&](int v) {
-        if (rmode == 1) return ws[L.grad + v] - ws[L.zl + v] + ws[L.zu + v];
-        double sg, r; sigma_r(v, &sg, &r); return r;
-      };
 #pragma unroll
-      for (int i = 0; i < NX; ++i) { pv[i] = rvar(ix(N, i)); ws[L.pp + N * NPP + NPX + i] = pv[i]; }
+      for (int i = 0; i < NX; ++i) { pv[i] = rvar(rmode, ix(N, i)); ws[L.pp + N * NPP + NPX + i] = pv[i]; }
+      BwdIn cur;
       for (int k = N - 1; k >= 0; --k) {
+        load_bwd(k, rmode, coff, cur);
+        if (k > 0) prefetch_bwd(k - 1, rmode, coff);
         double Pm[NX * NX], Pd[NX], gk[NU], t[NU];
-        load_P(k + 1, Pm);
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+#pragma unroll
+          for (int j = 0; j <= i; ++j) { const double v = cur.P[tri(i, j)]; Pm[i * NX + j] = v; Pm[j * NX + i] = v; }
+        }
         // Pd = P_{k+1} c_{k+1} + p_{k+1}
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
           double v = pv[i];
           if (coff >= 0) {
 #pragma unroll
-            for (int j = 0; j < NX; ++j) v += Pm[i * NX + j] * ws[coff + (k + 1) * NX + j];
+            for (int j = 0; j < NX; ++j) v += Pm[i * NX + j] * cur.c[j];
           }
           Pd[i] = v;
         }
-        const int ao = L.ab + k * NAB, ro = L.ric + k * NRIC;
+        const int ro = L.ric + k * NRIC;
         // g = r_u + B' Pd ; kff = -F^{-1} g
 #pragma unroll
         for (int i = 0; i < NU; ++i) {
-          double v = rvar(iu(k, i));
+          double v = cur.ru[i];
 #pragma unroll
-          for (int j = 0; j < NX; ++j) v += ws[ao + NX * NX + j * NU + i] * Pd[j];
+          for (int j = 0; j < NX; ++j) v += cur.B[j * NU + i] * Pd[j];
           if (bnd(iu(k, i)).fixed) v = 0.0;
           gk[i] = v;
         }
@@ -695,7 +941,7 @@ struct Ipm {
 #pragma unroll
         for (int i = 0; i < NU; ++i) {
 #pragma unroll
-          for (int j = 0; j <= i; ++j) F[i * NU + j] = ws[ro + NU * NX + NU + tri(i, j)];
+          for (int j = 0; j <= i; ++j) F[i * NU + j] = cur.F[tri(i, j)];
         }
 #pragma unroll
         for (int i = 0; i < NU; ++i) {
@@ -717,11 +963,11 @@ struct Ipm {
         double pk[NX];
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
-          double v = rvar(ix(k, i));
+          double v = cur.rx[i];
 #pragma unroll
-          for (int j = 0; j < NX; ++j) v += ws[ao + j * NX + i] * Pd[j];
+          for (int j = 0; j < NX; ++j) v += cur.A[j * NX + i] * Pd[j];
 #pragma unroll
-          for (int j = 0; j < NU; ++j) v += ws[ro + j * NX + i] * gk[j];
+          for (int j = 0; j < NU; ++j) v += cur.K[j * NX + i] * gk[j];
           pk[i] = v;
         }
 #pragma unroll
@@ -731,35 +977,41 @@ struct Ipm {
       double dx[NX];
 #pragma unroll
       for (int i = 0; i < NX; ++i) dx[i] = (coff >= 0) ? ws[coff + i] : 0.0;
+      FwdIn fc;
       for (int k = 0; k <= N; ++k) {
+        load_fwd(k, coff, fc);
+        if (k < N) prefetch_fwd(k + 1, coff);
         double Pm[NX * NX];
-        load_P(k, Pm);
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
-          double v = ws[L.pp + k * NPP + NPX + i];
+#pragma unroll
+          for (int j = 0; j <= i; ++j) { const double v = fc.P[tri(i, j)]; Pm[i * NX + j] = v; Pm[j * NX + i] = v; }
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+          double v = fc.p[i];
 #pragma unroll
           for (int j = 0; j < NX; ++j) v += Pm[i * NX + j] * dx[j];
           ws[L.lamp + k * NX + i] = v;
           ws[L.d + ix(k, i)] = dx[i];
         }
         if (k == N) break;
-        const int ao = L.ab + k * NAB, ro = L.ric + k * NRIC;
         double du[NU], dn[NX];
 #pragma unroll
         for (int i = 0; i < NU; ++i) {
-          double v = ws[ro + NU * NX + i];
+          double v = fc.kff[i];
 #pragma unroll
-          for (int j = 0; j < NX; ++j) v += ws[ro + i * NX + j] * dx[j];
+          for (int j = 0; j < NX; ++j) v += fc.K[i * NX + j] * dx[j];
           du[i] = v;
           ws[L.d + iu(k, i)] = v;
         }
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
-          double v = (coff >= 0) ? ws[coff + (k + 1) * NX + i] : 0.0;
+          double v = fc.c[i];
 #pragma unroll
-          for (int j = 0; j < NX; ++j) v += ws[ao + i * NX + j] * dx[j];
+          for (int j = 0; j < NX; ++j) v += fc.A[i * NX + j] * dx[j];
 #pragma unroll
-          for (int j = 0; j < NU; ++j) v += ws[ao + NX * NX + i * NU + j] * du[j];
+          for (int j = 0; j < NU; ++j) v += fc.B[i * NU + j] * du[j];
           dn[i] = v;
         }
 #pragma unroll
@@ -872,13 +1124,14 @@ struct Ipm {
   }
 
   // ---- step-length helpers ----------------------------------------------------------------------------
+  // dz = mu / s - z - (z / s) d  with one reciprocal per bound
   MPCV_D double dz_l(int i, const Bnd& b) const {
-    const double sl = ws[L.w + i] - b.lo;
-    return mu / sl - ws[L.zl + i] - ws[L.zl + i] / sl * ws[L.d + i];
+    const double inv = 1.0 / (ws[L.w + i] - b.lo), z = ws[L.zl + i];
+    return mu * inv - z - z * inv * ws[L.d + i];
   }
   MPCV_D double dz_u(int i, const Bnd& b) const {
-    const double su = b.hi - ws[L.w + i];
-    return mu / su - ws[L.zu + i] + ws[L.zu + i] / su * ws[L.d + i];
+    const double inv = 1.0 / (b.hi - ws[L.w + i]), z = ws[L.zu + i];
+    return mu * inv - z + z * inv * ws[L.d + i];
   }
   MPCV_D double ftb_primal() const {
     double a = 1.0;
@@ -890,14 +1143,24 @@ struct Ipm {
     }
     return g.min(a);
   }
+  // fraction-to-the-boundary rule for the bound multipliers.  The dual steps are parked in the (dead by
+  // now) Sigma / barrier-gradient slots for the update that follows.
   MPCV_D double ftb_dual() const {
     double a = 1.0;
     for (int i = g.lane; i < L.n; i += LANES) {
       const Bnd b = bnd(i);
-      if (b.hasl) { const double dz = dz_l(i, b); if (dz < 0.0) a = fmin(a, -tau * ws[L.zl + i] / dz); }
-      if (b.hasu) { const double dz = dz_u(i, b); if (dz < 0.0) a = fmin(a, -tau * ws[L.zu + i] / dz); }
+      if (b.hasl) { const double dz = dz_l(i, b); ws[L.sig + i] = dz; if (dz < 0.0) a = fmin(a, -tau * ws[L.zl + i] / dz); }
+      if (b.hasu) { const double dz = dz_u(i, b); ws[L.rb + i] = dz; if (dz < 0.0) a = fmin(a, -tau * ws[L.zu + i] / dz); }
     }
     return g.min(a);
+  }
+  // z reset into [mu / (kappa_Sigma s), kappa_Sigma mu / s], kappa_Sigma = 1e10 (a safeguard that almost
+  // never binds: test on z*s, divide only when it does)
+  MPCV_D double clamp_z(double z, double s) const {
+    const double zs = z * s;
+    if (zs > 1e10 * mu) return 1e10 * mu / s;
+    if (zs < mu / 1e10) return mu / (1e10 * s);
+    return z;
   }
 
   // mirror blocked controls from their predecessor so outputs read like MPCTools' u trajectory
@@ -908,12 +1171,16 @@ struct Ipm {
     g.sync();
   }
 
-  // ---- the solve ------------------------------------------------------------------------------------------
-  // On entry ws[L.w..] holds the starting point and ws[L.par..] the parameters.
-  MPCV_DN SolveInfo solve() {
-    SolveInfo info;
-    const double eps = 2.220446049250313e-16;
-    // push the starting point into the interior (bound_push / bound_frac); fixed variables take their value
+  // ---- the solve, phase by phase -----------------------------------------------------------------------
+  // The same phase functions are scheduled two ways: solve() runs them back to back inside one
+  // kernel (thread / warp layouts, closed loop); the phase-kernel pipeline (mpcv_phase.cuh) runs
+  // each phase as its own batch-wide launch with the scalar state parked in ws[L.st..].
+  //
+  // On entry to start() ws[L.w..] holds the starting point and ws[L.par..] the parameters.
+
+  // push the starting point into the interior (bound_push / bound_frac); fixed variables take
+  // their value; z0 = 1, lam0 = 0
+  MPCV_DN void start() {
     for (int i = g.lane; i < L.n; i += LANES) {
       const Bnd b = bnd(i);
       double v = ws[L.w + i];
@@ -934,23 +1201,34 @@ struct Ipm {
     for (int i = g.lane; i < NX * (N + 1); i += LANES) ws[L.lam + i] = 0.0;
     g.sync();
     sync_blocked();
-    // gradient-based objective scaling at the starting point (nlp_scaling_max_gradient)
     df = 1.0;
-    eval_derivatives(false);
-    {
-      double gmax = 0.0;
-      for (int i = g.lane; i < L.n; i += LANES)
-        if (!bnd(i).fixed) gmax = fmax(gmax, fabs(ws[L.grad + i]));
-      gmax = g.max(gmax);
-      if (gmax > P.scal_max_grad) {
-        df = fmax(P.scal_max_grad / gmax, 1e-8);
-        eval_derivatives(false);
-      }
-    }
     mu = P.mu_init;
     tau = fmax(0.99, 1.0 - mu);
     nfil = 0;
-    // least-squares multipliers  [I J'; J 0][.; lam] = -[grad f - zl + zu; 0]
+    theta_max = theta_min = -1.0;
+    delta_w_last = 0.0;
+    iter = 0;
+  }
+
+  // Precondition: eval_derivatives(false) at df = 1.  Gradient-based objective scaling
+  // (nlp_scaling_max_gradient) and least-squares multipliers  [I J'; J 0][.; lam] = -[grad f - zl + zu; 0]
+  MPCV_DN void init_scaling_and_multipliers() {
+    double gmax = 0.0;
+    for (int i = g.lane; i < L.n; i += LANES)
+      if (!bnd(i).fixed) gmax = fmax(gmax, fabs(ws[L.grad + i]));
+    gmax = g.max(gmax);
+    if (gmax > P.scal_max_grad) {
+      df = fmax(P.scal_max_grad / gmax, 1e-8);
+      if (SINGLE) {
+        eval_derivatives(false);
+      } else {
+        // grad and f are linear in df and were evaluated with df = 1: rescaling is bit-identical
+        // to a second derivative sweep
+        for (int i = g.lane; i < L.n; i += LANES) ws[L.grad + i] = df * ws[L.grad + i];
+        f_curr = df * f_curr;
+        g.sync();
+      }
+    }
     if (!SINGLE) {
       if (riccati_factor(0.0, true)) {
         riccati_solve(1, -1);
@@ -963,165 +1241,233 @@ struct Ipm {
         g.sync();
       }
     }
-    eval_derivatives(true);
+  }
 
-    double theta_max = -1.0, theta_min = -1.0, delta_w_last = 0.0;
-    int iter = 0;
-    info.status = MPCV_MAXIMUM_ITERATIONS_EXCEEDED;
-    for (;; ++iter) {
-      // --- convergence test ---
-      const Err e = errors();
-      const double E0 = Emu(e, 0.0);
-      {
-        const double dual_u = e.dual * e.sd / df, compl_u = compl_err(e, 0.0) * e.sc / df;
-        if (E0 <= P.tol && dual_u <= P.dual_inf_tol && e.prim <= P.constr_viol_tol && compl_u <= P.compl_inf_tol) {
-          info.status = MPCV_SOLVE_SUCCEEDED;
-          break;
+  // convergence test (scaled E_0 <= tol plus the unscaled caps) and monotone barrier update;
+  // returns a final IPOPT status or kRunning
+  MPCV_DN int check_convergence_update_mu() {
+    const Err e = errors();
+    const double E0 = Emu(e, 0.0);
+    {
+      const double dual_u = e.dual * e.sd / df, compl_u = compl_err(e, 0.0) * e.sc / df;
+      if (E0 <= P.tol && dual_u <= P.dual_inf_tol && e.prim <= P.constr_viol_tol && compl_u <= P.compl_inf_tol)
+        return MPCV_SOLVE_SUCCEEDED;
+    }
+    if (iter >= P.max_iter) return MPCV_MAXIMUM_ITERATIONS_EXCEEDED;
+    if (!(E0 < INFINITY)) return MPCV_INVALID_NUMBER_DETECTED;
+    bool done = false;
+    while (!done && Emu(e, mu) <= 10.0 * mu) {
+      double new_mu = fmin(0.2 * mu, pow(mu, 1.5));
+      new_mu = fmax(new_mu, fmin(P.tol, P.compl_inf_tol * df) / 11.0);
+      const bool changed = new_mu != mu;
+      mu = new_mu;
+      tau = fmax(0.99, 1.0 - mu);
+      if (!changed) done = true; else nfil = 0;
+    }
+    return kRunning;
+  }
+
+  // search direction with inertia correction, maximal primal step and the merit-function terms
+  // of the current iterate.  direction_first() tries delta_w = 0; direction_retry() walks IPOPT's
+  // delta_w schedule after a failed first attempt (the phase pipeline runs the retries as a separate,
+  // compacted launch so that warps without wrong inertia do not idle through them).
+  MPCV_DN bool direction_first() {
+    prepare_barrier();
+    const bool ok = SINGLE ? condensed_factor(0.0) : riccati_factor(0.0, false);
+    if (ok) direction_finish(0.0);
+    return ok;
+  }
+  // IPOPT's delta_w schedule: first trial 1e-4 (or a third of the last successful value), then x100
+  // (first correction ever / far above the last value) or x8
+  MPCV_D double next_delta_w(double dw) const {
+    if (dw == 0.0) return (delta_w_last == 0.0) ? 1e-4 : fmax(1e-20, delta_w_last / 3.0);
+    return dw * ((delta_w_last == 0.0 || 1e5 * delta_w_last < dw) ? 100.0 : 8.0);
+  }
+  // returns 0 or MPCV_ERROR_IN_STEP_COMPUTATION
+  MPCV_DN int direction_retry() {
+    double dw = 0.0;
+    bool ok = false;
+    while (!ok) {
+      dw = next_delta_w(dw);
+      if (dw > 1e20) break;
+      ok = SINGLE ? condensed_factor(dw) : riccati_factor(dw, false);
+    }
+    if (!ok) return MPCV_ERROR_IN_STEP_COMPUTATION;
+    direction_finish(dw);
+    return 0;
+  }
+  MPCV_D void direction_finish(double dw) {
+    if (dw > 0.0) delta_w_last = dw;
+    if (SINGLE) condensed_solve(); else riccati_solve(0, L.c);
+    direction_post();
+  }
+  // maximal primal step (fraction to the boundary) and the merit-function terms of the current iterate
+  MPCV_D void direction_post() {
+    ls_alpha_max = ftb_primal();
+    double theta = 0.0, gBD = 0.0, lg = 0.0;
+    for (int i = g.lane; i < L.m; i += LANES) theta += fabs(ws[L.c + i]);
+    for (int i = g.lane; i < L.n; i += LANES) {
+      double sg, r;
+      sigma_r(i, &sg, &r);
+      const Bnd b = bnd(i);
+      if (!b.fixed) gBD += r * ws[L.d + i];
+      if (b.hasl) lg += log(ws[L.w + i] - b.lo);
+      if (b.hasu) lg += log(b.hi - ws[L.w + i]);
+    }
+    theta = g.sum(theta); gBD = g.sum(gBD); lg = g.sum(lg);
+    ls_theta = theta;
+    ls_gBD = gBD;
+    ls_phi = f_curr - mu * lg;
+    if (theta_max < 0.0) { theta_max = 1e4 * fmax(1.0, theta); theta_min = 1e-4 * fmax(1.0, theta); }
+  }
+  MPCV_D int compute_direction() { return direction_first() ? 0 : direction_retry(); }
+
+  // ---- filter line search --------------------------------------------------------------------------------
+  // switching-condition powers of the current iterate, evaluated once per line search
+  struct LsPow { double g23, t11; };
+  MPCV_D LsPow ls_pows() const {
+    LsPow p;
+    p.g23 = ls_gBD < 0.0 ? pow(-ls_gBD, 2.3) : 0.0;
+    p.t11 = pow(ls_theta, 1.1);
+    return p;
+  }
+  MPCV_D bool ls_is_ftype(double a, const LsPow& pw) const {
+    const double eps = 2.220446049250313e-16;
+    if (ls_theta == 0.0 && ls_gBD > 0.0 && ls_gBD < 100.0 * eps) return true;
+    return ls_gBD < 0.0 && a * pw.g23 > pw.t11;
+  }
+  MPCV_D bool ls_armijo(double a, double phi_t) const { return compare_le(phi_t - ls_phi, 1e-8 * a * ls_gBD, ls_phi); }
+  MPCV_D bool ls_acceptable(double a, double phi_t, double theta_t, const LsPow& pw) const {
+    const double theta = ls_theta, phi = ls_phi;
+    if (!(phi_t < INFINITY) || !(theta_t < INFINITY) || phi_t != phi_t) return false;
+    if (theta_max > 0.0 && theta_t > theta_max) return false;
+    bool acc;
+    if (a > 0.0 && ls_is_ftype(a, pw) && theta <= theta_min) acc = ls_armijo(a, phi_t);
+    else {
+      if (phi_t > phi) {
+        double basval = 1.0;
+        if (fabs(phi) > 10.0) basval = log10(fabs(phi));
+        if (log10(phi_t - phi) > 5.0 + basval) return false;
+      }
+      acc = compare_le(theta_t, (1.0 - 1e-5) * theta, theta) || compare_le(phi_t - phi, -1e-8 * theta, phi);
+    }
+    if (!acc) return false;
+    for (int q = 0; q < nfil; ++q)
+      if (!(compare_le(phi_t, fil_phi[q], fil_phi[q]) || compare_le(theta_t, fil_th[q], fil_th[q]))) return false;
+    return true;
+  }
+  // filter augmentation, dual step length and the update of (w, z, lam) for an accepted step
+  MPCV_D void ls_accept_step(double alpha, double alpha_test, double phi_acc, const LsPow& pw) {
+    const double theta = ls_theta, phi = ls_phi;
+    if (!ls_is_ftype(alpha_test, pw) || !ls_armijo(alpha_test, phi_acc)) {
+      if (nfil < FILTER_MAX) {
+        fil_phi[nfil] = phi - 1e-8 * theta; fil_th[nfil] = (1.0 - 1e-5) * theta; ++nfil;
+      } else {
+        // filter full: drop the oldest entry
+        for (int q = 1; q < FILTER_MAX; ++q) { fil_phi[q - 1] = fil_phi[q]; fil_th[q - 1] = fil_th[q]; }
+        fil_phi[FILTER_MAX - 1] = phi - 1e-8 * theta; fil_th[FILTER_MAX - 1] = (1.0 - 1e-5) * theta;
+      }
+    }
+    const double alpha_dual = ftb_dual();
+    for (int i = g.lane; i < L.n; i += LANES) {
+      const Bnd b = bnd(i);
+      const double wi = ws[L.w + i] + alpha * ws[L.d + i];
+      ws[L.w + i] = wi;
+      if (b.hasl) ws[L.zl + i] = clamp_z(ws[L.zl + i] + alpha_dual * ws[L.sig + i], wi - b.lo);
+      if (b.hasu) ws[L.zu + i] = clamp_z(ws[L.zu + i] + alpha_dual * ws[L.rb + i], b.hi - wi);
+    }
+    if (!SINGLE)
+      for (int i = g.lane; i < L.m; i += LANES) ws[L.lam + i] += alpha * (ws[L.lamp + i] - ws[L.lam + i]);
+    g.sync();
+    sync_blocked();
+    ++iter;
+  }
+
+  // Fast path of the phase pipeline: the full step (alpha = ls_alpha_max, stage part already evaluated by
+  // trial_stage) is accepted by the filter — no backtracking, no second-order correction.  Returns false
+  // without touching the iterate when the slow path (line_search(true)) has to take over.
+  MPCV_DN bool line_search_first() {
+    const LsPow pw = ls_pows();
+    double f_t, theta_t, phi_t;
+    trial_reduce(ls_alpha_max, L.d, &f_t, &theta_t, &phi_t);
+    if (!ls_acceptable(ls_alpha_max, phi_t, theta_t, pw)) return false;
+    ls_accept_step(ls_alpha_max, ls_alpha_max, phi_t, pw);
+    return true;
+  }
+
+  // filter line search with second-order correction, then acceptance of the trial point
+  // (w, z, lam updated in place).  have_trial0: the stage part of the first trial (alpha =
+  // ls_alpha_max) was already evaluated by trial_stage().  Returns 0 or MPCV_RESTORATION_FAILED.
+  MPCV_DN int line_search(bool have_trial0) {
+    const LsPow pw = ls_pows();
+    const double alpha_max = ls_alpha_max, theta = ls_theta, gBD = ls_gBD;
+    double alpha_min = 1e-5;
+    if (gBD < 0.0) {
+      alpha_min = fmin(1e-5, 1e-8 * theta / (-gBD));
+      if (theta <= theta_min) alpha_min = fmin(alpha_min, pw.t11 / pw.g23);
+    }
+    alpha_min *= 0.05;
+    double alpha = alpha_max, alpha_test = alpha_max, phi_acc = 0.0;
+    bool accepted = false;
+    int nsteps = 0;
+    while (alpha > alpha_min || nsteps == 0) {
+      double f_t, theta_t, phi_t;
+      if (!SINGLE && have_trial0 && nsteps == 0) trial_reduce(alpha, L.d, &f_t, &theta_t, &phi_t);
+      else eval_trial(alpha, L.d, !SINGLE && nsteps == 0 && P.max_soc > 0, &f_t, &theta_t, &phi_t);
+      alpha_test = alpha;
+      if (ls_acceptable(alpha, phi_t, theta_t, pw)) { accepted = true; phi_acc = phi_t; break; }
+      // second-order correction on the first rejected trial
+      if (!SINGLE && nsteps == 0 && P.max_soc > 0 && theta_t >= theta) {
+        // c_soc accumulates in ct: c_soc = ct + alpha_soc * c_soc (c_soc starts as c)
+        double theta_soc_old = 0.0, theta_tr = theta_t, alpha_soc = alpha;
+        int count = 0;
+        bool acc_soc = false;
+        // save the plain direction so that a failed SOC can fall back to backtracking
+        save_step();
+        for (int i = g.lane; i < L.m; i += LANES) ws[L.ct + i] = ws[L.ct + i] + alpha_soc * ws[L.c + i];
+        g.sync();
+        while (count < P.max_soc && !acc_soc && (count == 0 || theta_tr <= 0.99 * theta_soc_old)) {
+          theta_soc_old = theta_tr;
+          riccati_solve(0, L.ct);
+          alpha_soc = ftb_primal();
+          double f_s, theta_s, phi_s;
+          eval_trial_soc(alpha_soc, &f_s, &theta_s, &phi_s);
+          if (ls_acceptable(alpha, phi_s, theta_s, pw)) { acc_soc = true; alpha = alpha_soc; phi_acc = phi_s; }
+          else { ++count; theta_tr = theta_s; }
         }
+        if (acc_soc) { accepted = true; break; }
+        restore_step();
       }
-      if (iter >= P.max_iter) { info.status = MPCV_MAXIMUM_ITERATIONS_EXCEEDED; break; }
-      if (!(E0 < INFINITY)) { info.status = MPCV_INVALID_NUMBER_DETECTED; break; }
-      // --- monotone barrier update ---
-      {
-        bool done = false;
-        while (!done && Emu(e, mu) <= 10.0 * mu) {
-          double new_mu = fmin(0.2 * mu, pow(mu, 1.5));
-          new_mu = fmax(new_mu, fmin(P.tol, P.compl_inf_tol * df) / 11.0);
-          const bool changed = new_mu != mu;
-          mu = new_mu;
-          tau = fmax(0.99, 1.0 - mu);
-          if (!changed) done = true; else nfil = 0;
-        }
-      }
-      // --- search direction with inertia correction ---
-      double dw = 0.0;
-      bool ok = SINGLE ? condensed_factor(0.0) : riccati_factor(0.0, false);
-      while (!ok) {
-        if (dw == 0.0) dw = (delta_w_last == 0.0) ? 1e-4 : fmax(1e-20, delta_w_last / 3.0);
-        else dw *= (delta_w_last == 0.0 || 1e5 * delta_w_last < dw) ? 100.0 : 8.0;
-        if (dw > 1e20) break;
-        ok = SINGLE ? condensed_factor(dw) : riccati_factor(dw, false);
-      }
-      if (!ok) { info.status = MPCV_ERROR_IN_STEP_COMPUTATION; break; }
-      if (dw > 0.0) delta_w_last = dw;
-      if (SINGLE) condensed_solve(); else riccati_solve(0, L.c);
-      double alpha_max = ftb_primal();
-      // --- filter line search ---
-      double theta = 0.0, gBD = 0.0, lg = 0.0;
-      for (int i = g.lane; i < L.m; i += LANES) theta += fabs(ws[L.c + i]);
-      for (int i = g.lane; i < L.n; i += LANES) {
-        double sg, r;
-        sigma_r(i, &sg, &r);
-        if (!bnd(i).fixed) gBD += r * ws[L.d + i];
-        const Bnd b = bnd(i);
-        if (b.hasl) lg += log(ws[L.w + i] - b.lo);
-        if (b.hasu) lg += log(b.hi - ws[L.w + i]);
-      }
-      theta = g.sum(theta); gBD = g.sum(gBD); lg = g.sum(lg);
-      const double phi = f_curr - mu * lg;
-      if (theta_max < 0.0) { theta_max = 1e4 * fmax(1.0, theta); theta_min = 1e-4 * fmax(1.0, theta); }
-      double alpha_min = 1e-5;
-      if (gBD < 0.0) {
-        alpha_min = fmin(1e-5, 1e-8 * theta / (-gBD));
-        if (theta <= theta_min) alpha_min = fmin(alpha_min, pow(theta, 1.1) / pow(-gBD, 2.3));
-      }
-      alpha_min *= 0.05;
-      auto is_ftype = [&](double a) {
-        if (theta == 0.0 && gBD > 0.0 && gBD < 100.0 * eps) return true;
-        return gBD < 0.0 && a * pow(-gBD, 2.3) > pow(theta, 1.1);
-      };
-      auto armijo = [&](double a, double phi_t) { return compare_le(phi_t - phi, 1e-8 * a * gBD, phi); };
-      auto acceptable = [&](double a, double phi_t, double theta_t) {
-        if (!(phi_t < INFINITY) || !(theta_t < INFINITY) || phi_t != phi_t) return false;
-        if (theta_max > 0.0 && theta_t > theta_max) return false;
-        bool acc;
-        if (a > 0.0 && is_ftype(a) && theta <= theta_min) acc = armijo(a, phi_t);
-        else {
-          if (phi_t > phi) {
-            double basval = 1.0;
-            if (fabs(phi) > 10.0) basval = log10(fabs(phi));
-            if (log10(phi_t - phi) > 5.0 + basval) return false;
-          }
-          acc = compare_le(theta_t, (1.0 - 1e-5) * theta, theta) || compare_le(phi_t - phi, -1e-8 * theta, phi);
-        }
-        if (!acc) return false;
-        for (int q = 0; q < nfil; ++q)
-          if (!(compare_le(phi_t, fil_phi[q], fil_phi[q]) || compare_le(theta_t, fil_th[q], fil_th[q]))) return false;
-        return true;
-      };
-      double alpha = alpha_max, alpha_test = alpha_max, phi_acc = 0.0;
-      bool accepted = false, soc_step = false;
-      int nsteps = 0;
-      while (alpha > alpha_min || nsteps == 0) {
-        double f_t, theta_t, phi_t;
-        eval_trial(alpha, L.d, !SINGLE && nsteps == 0 && P.max_soc > 0, &f_t, &theta_t, &phi_t);
-        alpha_test = alpha;
-        if (acceptable(alpha, phi_t, theta_t)) { accepted = true; phi_acc = phi_t; break; }
-        // second-order correction on the first rejected trial
-        if (!SINGLE && nsteps == 0 && P.max_soc > 0 && theta_t >= theta) {
-          // keep the plain step in lamp?  no: SOC overwrites d and lamp; save the plain step in grad-free slots
-          // c_soc accumulates in ct: c_soc = ct + alpha_soc * c_soc (c_soc starts as c)
-          double theta_soc_old = 0.0, theta_tr = theta_t, alpha_soc = alpha;
-          int count = 0;
-          bool acc_soc = false;
-          // save the plain direction so that a failed SOC can fall back to backtracking
-          save_step();
-          // csoc lives in ct: first  csoc = ct + alpha*c
-          for (int i = g.lane; i < L.m; i += LANES) ws[L.ct + i] = ws[L.ct + i] + alpha_soc * ws[L.c + i];
-          g.sync();
-          while (count < P.max_soc && !acc_soc && (count == 0 || theta_tr <= 0.99 * theta_soc_old)) {
-            theta_soc_old = theta_tr;
-            riccati_solve(0, L.ct);
-            alpha_soc = ftb_primal();
-            double f_s, theta_s, phi_s;
-            // trial residuals needed for a possible next correction: store into lamp-sized scratch (c slot is live) -> use tmp in pp? reuse ct after combining
-            eval_trial_soc(alpha_soc, &f_s, &theta_s, &phi_s);
-            if (acceptable(alpha, phi_s, theta_s)) { acc_soc = true; alpha = alpha_soc; phi_acc = phi_s; }
-            else { ++count; theta_tr = theta_s; }
-          }
-          if (acc_soc) { accepted = true; soc_step = true; break; }
-          restore_step();
-        }
-        alpha *= 0.5;
-        ++nsteps;
-      }
-      (void)soc_step;
-      if (!accepted) { info.status = MPCV_RESTORATION_FAILED; break; }
-      if (!is_ftype(alpha_test) || !armijo(alpha_test, phi_acc)) {
-        if (nfil < FILTER_MAX) {
-          fil_phi[nfil] = phi - 1e-8 * theta; fil_th[nfil] = (1.0 - 1e-5) * theta; ++nfil;
-        } else {
-          // filter full: overwrite the entry dominated most weakly (oldest)
-          for (int q = 1; q < FILTER_MAX; ++q) { fil_phi[q - 1] = fil_phi[q]; fil_th[q - 1] = fil_th[q]; }
-          fil_phi[FILTER_MAX - 1] = phi - 1e-8 * theta; fil_th[FILTER_MAX - 1] = (1.0 - 1e-5) * theta;
-        }
-      }
-      const double alpha_dual = ftb_dual();
-      // --- accept the trial point ---
-      for (int i = g.lane; i < L.n; i += LANES) {
-        const Bnd b = bnd(i);
-        const double dzl = b.hasl ? dz_l(i, b) : 0.0, dzu = b.hasu ? dz_u(i, b) : 0.0;
-        const double wi = ws[L.w + i] + alpha * ws[L.d + i];
-        ws[L.w + i] = wi;
-        if (b.hasl) {
-          const double sl = wi - b.lo;
-          double z = ws[L.zl + i] + alpha_dual * dzl;
-          z = fmax(fmin(z, 1e10 * mu / sl), mu / (1e10 * sl));
-          ws[L.zl + i] = z;
-        }
-        if (b.hasu) {
-          const double su = b.hi - wi;
-          double z = ws[L.zu + i] + alpha_dual * dzu;
-          z = fmax(fmin(z, 1e10 * mu / su), mu / (1e10 * su));
-          ws[L.zu + i] = z;
-        }
-      }
-      if (!SINGLE)
-        for (int i = g.lane; i < L.m; i += LANES) ws[L.lam + i] += alpha * (ws[L.lamp + i] - ws[L.lam + i]);
-      g.sync();
-      sync_blocked();
+      alpha *= 0.5;
+      ++nsteps;
+    }
+    if (!accepted) return MPCV_RESTORATION_FAILED;
+    ls_accept_step(alpha, alpha_test, phi_acc, pw);
+    return 0;
+  }
+
+  MPCV_DN SolveInfo solve() {
+    SolveInfo info;
+    start();
+    eval_derivatives(false);
+    init_scaling_and_multipliers();
+    eval_derivatives(true);
+    for (;;) {
+      int st = check_convergence_update_mu();
+      if (st != kRunning) { info.status = st; break; }
+      st = compute_direction();
+      if (st == 0) st = line_search(false);
+      if (st != 0) { info.status = st; break; }
       eval_derivatives(true);
     }
+    info.iters = iter;
+    info.f = f_curr / df;
+    info.df = df;
+    return info;
+  }
+  MPCV_D SolveInfo finish(int status) const {
+    SolveInfo info;
+    info.status = status;
     info.iters = iter;
     info.f = f_curr / df;
     info.df = df;

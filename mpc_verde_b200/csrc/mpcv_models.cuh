@@ -21,7 +21,12 @@
 #define MPCV_D __device__ __forceinline__
 // heavy phases of the interior-point iteration are real calls: one copy of each in the
 // instruction stream keeps the kernel inside the instruction cache
+#if defined(MPCV_INLINE_PHASES)
+// phase-kernel translation units: every kernel holds one or two phases, inline them
+#define MPCV_DN __device__ __forceinline__
+#else
 #define MPCV_DN __device__ __noinline__
+#endif
 #else
 #define MPCV_HD inline
 #define MPCV_D inline

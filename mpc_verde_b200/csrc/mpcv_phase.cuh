@@ -1,0 +1,462 @@
+// mpcv_phase.cuh — batch-synchronous phase pipeline for the multiple-shooting solve.
+//
+// Replaces the same reference call as mpcv_ipm.cuh (`sol = solver(x0=,lbx=,ubx=,lbg=,ubg=,p=)`,
+// Casadi/multiple_shooting_casadi.py:235-242; `solver.solve()` of the MPCTools scripts) and runs
+// exactly the phase functions of Ipm<Model,false,1,WsStrided> — but each phase is its own
+// batch-wide launch, so that
+//   * every warp of the GPU executes the same small piece of code at the same time (the one-kernel
+//     solve thrashes the 32 KB instruction cache: its iteration body is ~200 KB of SASS),
+//   * each phase gets the parallel decomposition that fits it: the derivative sweep and the
+//     line-search trial evaluation are independent per shooting interval and run one thread per
+//     (problem, interval); the Riccati recursion is sequential over the horizon and runs one thread
+//     per problem,
+//   * finished problems leave the batch: an active list is compacted every iteration
+//     (warp-aggregated atomics), so lanes never idle on problems that have converged,
+//   * registers are allocated per phase instead of for the union of all phases.
+// The per-problem workspace is the structure-of-arrays slab of the thread layout (element i of
+// problem b at slab[(b/32)*32*total + i*32 + b%32]); the scalar state of a solve (mu, tau, filter, ...) is parked in
+// ws[L.st ..] between launches.
+//
+// One interior-point iteration = pre -> factor -> retry -> post -> trial -> accept -> slow -> der -> flip:
+//   pre     8 lanes / problem     error measures, convergence test (exports finished problems), barrier
+//                                 update, Sigma / barrier gradient; ordered compaction of the active list
+//   factor  thread per problem    Riccati factorisation with delta_w = 0 + vector recursions
+//   retry   thread per problem    IPOPT's delta_w schedule, only over the problems with wrong inertia
+//   post    8 lanes / problem     fraction-to-the-boundary step, merit-function terms
+//   trial   thread per (problem, interval)   first line-search trial point
+//   accept  8 lanes / problem     filter test of the full step, dual step, update of (w, z, lambda)
+//   slow    warp per problem      backtracking / second-order correction, only over rejected problems
+//   der     thread per (problem, interval)   derivative sweep at the new iterate
+//   flip    one thread            list swap, loop condition of the WHILE node
+// The sequential recursions run one thread per problem (every lane busy, coalesced rows of the blocked
+// slab); everything that is parallel over variables or intervals runs with 32x or 10x more threads so
+// that HBM latency is hidden by parallelism instead of being serialised inside one thread.
+// The whole solve is ONE CUDA graph whose iteration body sits in a conditional WHILE node, so
+// mpcv_solve stays asynchronous on the caller's stream (no host round trip per iteration).
+//
+// The per-thread bodies below are plain functions shared by the CUDA kernels and by the CPU
+// development harness (tests/hostsim), which replays the same schedule with one lane per problem.
+#pragma once
+
+#include "mpcv_driver.cuh"
+
+namespace mpcv {
+
+struct PhaseCtrl {
+  int n_act[2];   // entries of the two ping-pong active lists
+  int sweep;      // iteration sweeps done; list (sweep & 1) is the input of the next newton phase
+  int B;          // problems of this call
+  int sweeps_total;
+  int n_retry;    // problems whose first factorisation had the wrong inertia (this sweep)
+  int n_slow;     // problems whose full step was rejected by the filter (this sweep)
+  int sweeps_cum; // sweeps since the handle was created (launch accounting)
+};
+
+template <class Model, class WS, int LANES = 1>
+struct Phase {
+  using IpmT = Ipm<Model, false, LANES, WS>;
+  using Ipm1 = Ipm<Model, false, 1, WS>;
+  static constexpr int NX = Model::NX, NH = Model::NX + Model::NPG;
+
+  // load x0 / p, push into the interior, z0, lam0; state := running            (thread per problem)
+  MPCV_HD static void init_body(const Params& P, const Layout& L, WS ws, const SolveIO& io, long b,
+                                const BndEntry* tab, long long t0) {
+    const int np = NH + L.N * Model::NPS;
+    for (int i = 0; i < L.n; ++i) ws[L.w + i] = io.x0 ? io.x0[b * L.n + i] : 0.0;
+    for (int i = 0; i < np; ++i) ws[L.par + i] = io.p[b * np + i];
+    Ipm1 ipm(P, L, ws, Grp<1>(0), io.lbx, io.ubx, tab);
+    ipm.start();
+    ipm.save_state(kRunning);
+    ws[L.st + 14] = long_as_double(t0);
+  }
+
+  // derivative sweep, one shooting interval                                   (thread per interval)
+  MPCV_HD static void der_body(const Params& P, const Layout& L, WS ws, const SolveIO& io, int k, bool want_hess,
+                               const BndEntry* tab) {
+    Ipm1 ipm(P, L, ws, Grp<1>(0), io.lbx, io.ubx, tab);
+    ipm.df = ws[L.st + 0];
+    ws[L.qs + k] = ipm.der_stage(k, want_hess);
+    if (k == 0) ipm.der_terminal();
+  }
+
+  // objective scaling + least-squares multipliers (after the first derivative sweep at df = 1)
+  MPCV_HD static void init2_body(const Params& P, const Layout& L, WS ws, const SolveIO& io, const BndEntry* tab) {
+    Ipm1 ipm(P, L, ws, Grp<1>(0), io.lbx, io.ubx, tab);
+    ipm.load_state();
+    ipm.f_curr = ipm.sum_stage_costs();
+    ipm.init_scaling_and_multipliers();
+    ipm.save_state(kRunning);
+  }
+
+  // convergence test, barrier update, Sigma and barrier gradient.  Returns true when the problem stays
+  // active; otherwise it is finished and its solution has been exported.        (LANES lanes per problem)
+  MPCV_HD static bool pre_body(const Params& P, const Layout& L, WS ws, const SolveIO& io, long b,
+                               const BndEntry* tab, Grp<LANES> g, long long now) {
+    IpmT ipm(P, L, ws, g, io.lbx, io.ubx, tab);
+    int st = ipm.load_state();
+    if (st != kRunning) return false;                 // failed earlier in this solve: already exported
+    ipm.f_curr = ipm.sum_stage_costs();
+    st = ipm.check_convergence_update_mu();
+    if (st != kRunning) {
+      finish(ipm, st, io, b, now);
+      return false;
+    }
+    ipm.prepare_barrier();
+    ipm.save_state(kRunning);
+    return true;
+  }
+
+  // Riccati factorisation with delta_w = 0 and, when the inertia is right, the vector recursions.
+  // Returns false when the delta_w schedule has to take over.                    (thread per problem)
+  MPCV_HD static bool factor_body(const Params& P, const Layout& L, WS ws, const SolveIO& io, const BndEntry* tab) {
+    Ipm1 ipm(P, L, ws, Grp<1>(0), io.lbx, io.ubx, tab);
+    if (!ipm.riccati_factor(0.0, false)) return false;
+    ipm.riccati_solve(0, L.c);
+    return true;
+  }
+
+  // inertia-correction retries (IPOPT's delta_w schedule)                       (thread per problem)
+  MPCV_HD static void retry_body(const Params& P, const Layout& L, WS ws, const SolveIO& io, long b,
+                                 const BndEntry* tab, long long now) {
+    Ipm1 ipm(P, L, ws, Grp<1>(0), io.lbx, io.ubx, tab);
+    ipm.delta_w_last = ws[L.st + 6];
+    double dw = 0.0;
+    bool ok = false;
+    while (!ok) {
+      dw = ipm.next_delta_w(dw);
+      if (dw > 1e20) break;
+      ok = ipm.riccati_factor(dw, false);
+    }
+    if (!ok) {
+      ipm.load_state();
+      finish(ipm, MPCV_ERROR_IN_STEP_COMPUTATION, io, b, now);
+      return;
+    }
+    ws[L.st + 6] = dw;
+    ipm.riccati_solve(0, L.c);
+  }
+
+  MPCV_HD static bool running(const Layout& L, WS ws) { return (int)ws[L.st + 9] == kRunning; }
+
+  // fraction-to-the-boundary step and merit-function terms                      (LANES lanes per problem)
+  MPCV_HD static void post_body(const Params& P, const Layout& L, WS ws, const SolveIO& io, const BndEntry* tab,
+                                Grp<LANES> g) {
+    IpmT ipm(P, L, ws, g, io.lbx, io.ubx, tab);
+    ipm.load_state();
+    ipm.direction_post();
+    ipm.save_state(kRunning);
+  }
+
+  // first line-search trial point, one shooting interval                         (thread per interval)
+  MPCV_HD static void trial_body(const Params& P, const Layout& L, WS ws, const SolveIO& io, int k,
+                                 const BndEntry* tab) {
+    Ipm1 ipm(P, L, ws, Grp<1>(0), io.lbx, io.ubx, tab);
+    ipm.trial_stage(k, ws[L.st + 10], L.d);
+  }
+
+  // fast path of the line search: the full step passes the filter.  Returns false when the problem needs
+  // the slow path (nothing has been modified then).                              (LANES lanes per problem)
+  MPCV_HD static bool accept_body(const Params& P, const Layout& L, WS ws, const SolveIO& io, const BndEntry* tab,
+                                  Grp<LANES> g) {
+    IpmT ipm(P, L, ws, g, io.lbx, io.ubx, tab);
+    ipm.load_state();
+    if (!ipm.line_search_first()) return false;
+    ipm.save_state(kRunning);
+    return true;
+  }
+
+  // slow path: backtracking and second-order correction                          (LANES lanes per problem)
+  MPCV_HD static void slow_body(const Params& P, const Layout& L, WS ws, const SolveIO& io, long b,
+                                const BndEntry* tab, Grp<LANES> g, long long now) {
+    IpmT ipm(P, L, ws, g, io.lbx, io.ubx, tab);
+    ipm.load_state();
+    const int st = ipm.line_search(true);
+    if (st != 0) { finish(ipm, st, io, b, now); return; }
+    ipm.save_state(kRunning);
+  }
+
+  template <class I>
+  MPCV_HD static void finish(I& ipm, int status, const SolveIO& io, long b, long long now) {
+    const SolveInfo info = ipm.finish(status);
+    export_solution(ipm, info, io, b);
+    ipm.save_state(status);
+    if (io.ns && ipm.g.lane == 0) io.ns[b] = now - double_as_long(ipm.ws[ipm.L.st + 14]);
+  }
+
+  MPCV_HD static double long_as_double(long long v) {
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double(v);
+#else
+    double d; memcpy(&d, &v, sizeof d); return d;
+#endif
+  }
+  MPCV_HD static long long double_as_long(double d) {
+#if defined(__CUDA_ARCH__)
+    return __double_as_longlong(d);
+#else
+    long long v; memcpy(&v, &d, sizeof v); return v;
+#endif
+  }
+};
+
+#if defined(__CUDACC__)
+// ---------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ long long ph_globaltimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// cooperative fill of the relaxed-bounds table in dynamic shared memory
+template <class Model>
+__device__ __forceinline__ const BndEntry* ph_bounds_table(const Params& P, const Layout& L, const SolveIO& io) {
+  extern __shared__ __align__(16) unsigned char ph_smem[];
+  BndEntry* tab = reinterpret_cast<BndEntry*>(ph_smem);
+  Ipm<Model, false, 1, WsStrided> ipm(P, L, WsStrided{nullptr}, Grp<1>(0), io.lbx, io.ubx, nullptr);
+  for (int i = threadIdx.x; i < L.n; i += blockDim.x) tab[i] = ipm.bnd_entry(i);
+  __syncthreads();
+  return tab;
+}
+
+struct PhaseArgs {
+  Params P;
+  Layout L;
+  double* slab;
+  int* act[2];
+  int* retry;          // problems needing inertia-correction retries this sweep
+  int* slow;           // problems needing the slow line-search path this sweep
+  PhaseCtrl* ctrl;
+  const SolveIO* io;   // device copy of the call's I/O pointers
+  long cap;            // problems the lists and the slab are sized for
+};
+
+constexpr int kPhaseThreads = 128;       // thread-per-problem / thread-per-interval kernels
+constexpr int kWarpPhaseThreads = 256;   // lane-group kernels
+// pre / post / accept: 8 lanes per problem, the 4 problems of a warp being neighbours in the active list.
+// Scalar work (pow, filter logic, state hand-over) is then shared by 4 problems per warp instruction, and
+// a warp-load touches 8 whole sectors: the 4 neighbouring problems share each 32-byte sector of the slab.
+constexpr int kGroupLanes = 8;
+
+// Every phase kernel is launched with a FIXED grid (the launches are nodes of a CUDA graph) sized to
+// fill the GPU once, and strides over its work list: a sweep that has three problems left costs a few
+// microseconds per launch instead of a full grid of CTAs that start only to exit.
+
+template <class Model>
+__global__ void __launch_bounds__(kPhaseThreads) ph_init_kernel(const __grid_constant__ PhaseArgs a) {
+  const SolveIO io = *a.io;
+  const BndEntry* tab = ph_bounds_table<Model>(a.P, a.L, io);
+  const long B = a.ctrl->B;
+  for (long b = (long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long)gridDim.x * blockDim.x) {
+    a.act[0][b] = (int)b;
+    Phase<Model, WsStrided>::init_body(a.P, a.L, WsStrided::of(a.slab, a.L.total, b), io, b, tab,
+                                       io.ns ? ph_globaltimer() : 0);
+  }
+}
+
+// first derivative sweeps (all problems): thread per (problem, interval)
+template <class Model>
+__global__ void __launch_bounds__(kPhaseThreads) ph_der0_kernel(const __grid_constant__ PhaseArgs a, int want_hess) {
+  const SolveIO io = *a.io;
+  const BndEntry* tab = ph_bounds_table<Model>(a.P, a.L, io);
+  const long B = a.ctrl->B, items = B * a.L.N;
+  for (long it = (long)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (long)gridDim.x * blockDim.x) {
+    const long b = it % B;
+    const int k = (int)(it / B);
+    Phase<Model, WsStrided>::der_body(a.P, a.L, WsStrided::of(a.slab, a.L.total, b), io, k, want_hess != 0, tab);
+  }
+}
+
+template <class Model>
+__global__ void __launch_bounds__(kPhaseThreads) ph_init2_kernel(const __grid_constant__ PhaseArgs a) {
+  const SolveIO io = *a.io;
+  const BndEntry* tab = ph_bounds_table<Model>(a.P, a.L, io);
+  const long B = a.ctrl->B;
+  for (long b = (long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long)gridDim.x * blockDim.x)
+    Phase<Model, WsStrided>::init2_body(a.P, a.L, WsStrided::of(a.slab, a.L.total, b), io, tab);
+}
+
+// warp-aggregated append of the flagged lanes' problem indices to a list (order kept within the warp)
+__device__ __forceinline__ void ph_append(bool flag, int b, int* list, int* count) {
+  const unsigned m = __ballot_sync(0xffffffffu, flag);
+  if (m) {
+    const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(count, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (flag) list[base + __popc(m & ((1u << lane) - 1u))] = b;
+  }
+}
+
+// pre: one warp per problem.  The surviving problems of a CTA pass are appended to the output list as
+// ONE contiguous, order-preserving run, so the thread-per-problem Riccati kernels that follow keep
+// reading neighbouring problems in neighbouring lanes (whole 32-byte sectors of the blocked slab).
+template <class Model>
+__global__ void __launch_bounds__(kWarpPhaseThreads, 3) ph_pre_kernel(const __grid_constant__ PhaseArgs a) {
+  constexpr int GPB = kWarpPhaseThreads / kGroupLanes;   // problems per CTA pass (32)
+  static_assert(GPB <= 32, "one ballot covers the CTA's problems");
+  __shared__ int keep_s[GPB], b_s[GPB], base_s;
+  const int in = a.ctrl->sweep & 1, out = in ^ 1;
+  const int n_in = a.ctrl->n_act[in];
+  const int wpb = GPB, warp = threadIdx.x / kGroupLanes, lane = threadIdx.x & 31;
+  const Grp<kGroupLanes> g(lane);
+  if ((long)blockIdx.x * wpb >= n_in) return;
+  const SolveIO io = *a.io;
+  const BndEntry* tab = ph_bounds_table<Model>(a.P, a.L, io);
+  for (long e0 = (long)blockIdx.x * wpb; e0 < n_in; e0 += (long)gridDim.x * wpb) {
+    const long e = e0 + warp;
+    bool keep = false;
+    int b = 0;
+    if (e < n_in) {
+      b = a.act[in][e];
+      keep = Phase<Model, WsStrided, kGroupLanes>::pre_body(a.P, a.L, WsStrided::of(a.slab, a.L.total, b), io, b, tab, g,
+                                                            io.ns ? ph_globaltimer() : 0);
+    }
+    if (g.lane == 0) { keep_s[warp] = keep ? 1 : 0; b_s[warp] = b; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const bool k = lane < wpb && keep_s[lane] != 0;
+      const unsigned m = __ballot_sync(0xffffffffu, k);
+      if (lane == 0) base_s = m ? atomicAdd(&a.ctrl->n_act[out], __popc(m)) : 0;
+      __syncwarp();
+      if (k) a.act[out][base_s + __popc(m & ((1u << lane) - 1u))] = b_s[lane];
+    }
+    __syncthreads();
+  }
+}
+
+template <class Model>
+__global__ void __launch_bounds__(kPhaseThreads, 4) ph_factor_kernel(const __grid_constant__ PhaseArgs a) {
+  const int out = (a.ctrl->sweep & 1) ^ 1;
+  const int n = a.ctrl->n_act[out];
+  if ((long)blockIdx.x * blockDim.x >= n) return;
+  const SolveIO io = *a.io;
+  const BndEntry* tab = ph_bounds_table<Model>(a.P, a.L, io);
+  for (long e0 = (long)blockIdx.x * blockDim.x; e0 < n; e0 += (long)gridDim.x * blockDim.x) {
+    const long e = e0 + threadIdx.x;
+    bool retry = false;
+    int b = 0;
+    if (e < n) {
+      b = a.act[out][e];
+      retry = !Phase<Model, WsStrided>::factor_body(a.P, a.L, WsStrided::of(a.slab, a.L.total, b), io, tab);
+    }
+    ph_append(retry, b, a.retry, &a.ctrl->n_retry);
+  }
+}
+
+template <class Model>
+__global__ void __launch_bounds__(kPhaseThreads, 4) ph_retry_kernel(const __grid_constant__ PhaseArgs a) {
+  const int n = a.ctrl->n_retry;
+  if ((long)blockIdx.x * blockDim.x >= n) return;
+  const SolveIO io = *a.io;
+  const BndEntry* tab = ph_bounds_table<Model>(a.P, a.L, io);
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) {
+    const int b = a.retry[e];
+    Phase<Model, WsStrided>::retry_body(a.P, a.L, WsStrided::of(a.slab, a.L.total, b), io, b, tab,
+                                        io.ns ? ph_globaltimer() : 0);
+  }
+}
+
+template <class Model>
+__global__ void __launch_bounds__(kWarpPhaseThreads, 3) ph_post_kernel(const __grid_constant__ PhaseArgs a) {
+  const int out = (a.ctrl->sweep & 1) ^ 1;
+  const int n = a.ctrl->n_act[out];
+  const int wpb = blockDim.x / kGroupLanes, warp = threadIdx.x / kGroupLanes;
+  const Grp<kGroupLanes> g(threadIdx.x & 31);
+  if ((long)blockIdx.x * wpb >= n) return;
+  const SolveIO io = *a.io;
+  const BndEntry* tab = ph_bounds_table<Model>(a.P, a.L, io);
+  for (long e = (long)blockIdx.x * wpb + warp; e < n; e += (long)gridDim.x * wpb) {
+    const int b = a.act[out][e];
+    const WsStrided ws = WsStrided::of(a.slab, a.L.total, b);
+    if (!Phase<Model, WsStrided>::running(a.L, ws)) continue;     // retries exhausted: already exported
+    Phase<Model, WsStrided, kGroupLanes>::post_body(a.P, a.L, ws, io, tab, g);
+  }
+}
+
+template <class Model>
+__global__ void __launch_bounds__(kPhaseThreads) ph_trial_kernel(const __grid_constant__ PhaseArgs a) {
+  const int out = (a.ctrl->sweep & 1) ^ 1;
+  const long n = a.ctrl->n_act[out], items = n * a.L.N;
+  if ((long)blockIdx.x * blockDim.x >= items) return;
+  const SolveIO io = *a.io;
+  const BndEntry* tab = ph_bounds_table<Model>(a.P, a.L, io);
+  for (long it = (long)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (long)gridDim.x * blockDim.x) {
+    const int b = a.act[out][it % n];
+    const int k = (int)(it / n);
+    const WsStrided ws = WsStrided::of(a.slab, a.L.total, b);
+    if (!Phase<Model, WsStrided>::running(a.L, ws)) continue;
+    Phase<Model, WsStrided>::trial_body(a.P, a.L, ws, io, k, tab);
+  }
+}
+
+template <class Model>
+__global__ void __launch_bounds__(kWarpPhaseThreads, 3) ph_accept_kernel(const __grid_constant__ PhaseArgs a) {
+  const int out = (a.ctrl->sweep & 1) ^ 1;
+  const int n = a.ctrl->n_act[out];
+  const int wpb = blockDim.x / kGroupLanes, warp = threadIdx.x / kGroupLanes;
+  const Grp<kGroupLanes> g(threadIdx.x & 31);
+  if ((long)blockIdx.x * wpb >= n) return;
+  const SolveIO io = *a.io;
+  const BndEntry* tab = ph_bounds_table<Model>(a.P, a.L, io);
+  for (long e = (long)blockIdx.x * wpb + warp; e < n; e += (long)gridDim.x * wpb) {
+    const int b = a.act[out][e];
+    const WsStrided ws = WsStrided::of(a.slab, a.L.total, b);
+    if (!Phase<Model, WsStrided>::running(a.L, ws)) continue;
+    const bool ok = Phase<Model, WsStrided, kGroupLanes>::accept_body(a.P, a.L, ws, io, tab, g);
+    if (!ok && g.lane == 0) a.slow[atomicAdd(&a.ctrl->n_slow, 1)] = b;
+  }
+}
+
+template <class Model>
+__global__ void __launch_bounds__(kWarpPhaseThreads) ph_slow_kernel(const __grid_constant__ PhaseArgs a) {
+  const int n = a.ctrl->n_slow;
+  const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((long)blockIdx.x * wpb >= n) return;
+  const SolveIO io = *a.io;
+  const BndEntry* tab = ph_bounds_table<Model>(a.P, a.L, io);
+  for (long e = (long)blockIdx.x * wpb + warp; e < n; e += (long)gridDim.x * wpb) {
+    const int b = a.slow[e];
+    Phase<Model, WsStrided, 32>::slow_body(a.P, a.L, WsStrided::of(a.slab, a.L.total, b), io, b, tab,
+                                           Grp<32>(lane), io.ns ? ph_globaltimer() : 0);
+  }
+}
+
+template <class Model>
+__global__ void __launch_bounds__(kPhaseThreads) ph_der_kernel(const __grid_constant__ PhaseArgs a) {
+  const int out = (a.ctrl->sweep & 1) ^ 1;
+  const long n = a.ctrl->n_act[out], items = n * a.L.N;
+  if ((long)blockIdx.x * blockDim.x >= items) return;
+  const SolveIO io = *a.io;
+  const BndEntry* tab = ph_bounds_table<Model>(a.P, a.L, io);
+  for (long it = (long)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (long)gridDim.x * blockDim.x) {
+    const int b = a.act[out][it % n];
+    const int k = (int)(it / n);
+    const WsStrided ws = WsStrided::of(a.slab, a.L.total, b);
+    if (!Phase<Model, WsStrided>::running(a.L, ws)) continue;   // failed this sweep: nothing to refresh
+    Phase<Model, WsStrided>::der_body(a.P, a.L, ws, io, k, true, tab);
+  }
+}
+
+// end of an iteration sweep: swap the lists and tell the WHILE node whether anyone is left
+static __global__ void ph_flip_kernel(PhaseCtrl* ctrl, cudaGraphConditionalHandle handle, int use_handle) {
+  const int in = ctrl->sweep & 1, out = in ^ 1;
+  ctrl->n_act[in] = 0;
+  ctrl->n_retry = 0;
+  ctrl->n_slow = 0;
+  ctrl->sweep += 1;
+  ctrl->sweeps_total += 1;
+  ctrl->sweeps_cum += 1;
+  if (use_handle) cudaGraphSetConditional(handle, ctrl->n_act[out] > 0 ? 1u : 0u);
+}
+
+static __global__ void ph_begin_kernel(PhaseCtrl* ctrl, SolveIO* dst, const SolveIO io, int B) {
+  *dst = io;
+  ctrl->B = B;
+  ctrl->n_act[0] = B; ctrl->n_act[1] = 0; ctrl->sweep = 0; ctrl->sweeps_total = 0;
+  ctrl->n_retry = 0; ctrl->n_slow = 0;
+}
+#endif  // __CUDACC__
+
+}  // namespace mpcv

@@ -83,6 +83,24 @@ class NlpSolver:
     def launch_count(self):
         return int(self._handle.lib.mpcv_launch_count(self._handle.h))
 
+    def _phase_counts(self):
+        import ctypes as C
+        n, k = C.c_int32(0), C.c_int64(0)
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(self._handle.lib.mpcv_phase_sweeps(self._handle.h, C.byref(n), C.byref(k), C.c_void_p(st)),
+                       "mpcv_phase_sweeps")
+        return int(n.value), int(k.value)
+
+    def phase_sweeps(self):
+        """Interior-point sweeps the last phased-layout solve ran on the device (each sweep is nine
+        kernel nodes of the solve's CUDA graph).  Synchronises the current stream."""
+        return self._phase_counts()[0]
+
+    def kernel_count(self):
+        """Kernels run through this handle since creation, graph-driven sweeps included."""
+        return self._phase_counts()[1]
+
     # -- argument normalisation ---------------------------------------------------------------
     def _vec(self, a, n, fill, name, device):
         """bounds: scalar-broadcast allowed (e.g. lbg=-inf, single_shooting_v1.py:141)."""

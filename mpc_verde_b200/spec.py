@@ -25,6 +25,7 @@ WARM_REFERENCE = 2
 LAYOUT_AUTO = 0
 LAYOUT_THREAD = 1
 LAYOUT_WARP = 2
+LAYOUT_PHASED = 3
 
 # IPOPT ApplicationReturnStatus names, as CasADi reports them in solver.stats()['return_status']
 STATUS_NAMES = {

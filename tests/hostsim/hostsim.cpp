@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../mpc_verde_b200/csrc/mpcv_driver.cuh"
+#include "../../mpc_verde_b200/csrc/mpcv_phase.cuh"
 #include "../../mpc_verde_b200/csrc/mpcv_params.h"
 
 using namespace mpcv;
@@ -20,6 +21,61 @@ static int hs_solve_t(const mpcv_spec* s, const SolveIO& io, long B) {
     std::fill(buf.begin(), buf.end(), 0.0);
     solve_problem<Model, SINGLE, 1, WsDense>(P, L, WsDense{buf.data()}, Grp<1>(0), io, b);
   }
+  return 0;
+}
+
+// The phase-kernel pipeline (mpcv_phase.cuh) replayed sequentially: the same per-thread bodies in the
+// same order as the CUDA graph issues them, including the ping-pong active lists.
+template <class Model>
+static int hs_solve_phased_t(const mpcv_spec* s, const SolveIO& io, long B, int* sweeps_out) {
+  using Ph = Phase<Model, WsDense>;
+  Params P = params_from_spec(*s);
+  Layout L = make_layout<Model, false>(s->N);
+  std::vector<double> slab((size_t)L.total * B, 0.0);
+  auto ws = [&](long b) { return WsDense{slab.data() + (size_t)b * L.total}; };
+  std::vector<BndEntry> tab(L.n);
+  {
+    Ipm<Model, false, 1, WsDense> ipm(P, L, WsDense{nullptr}, Grp<1>(0), io.lbx, io.ubx, nullptr);
+    for (int i = 0; i < L.n; ++i) tab[i] = ipm.bnd_entry(i);
+  }
+  std::vector<int> act[2];
+  act[0].resize(B); act[1].resize(B);
+  int n_act[2] = {(int)B, 0}, sweep = 0;
+  for (long b = 0; b < B; ++b) { act[0][b] = (int)b; Ph::init_body(P, L, ws(b), io, b, tab.data(), 0); }
+  for (int k = 0; k < L.N; ++k) for (long b = 0; b < B; ++b) Ph::der_body(P, L, ws(b), io, k, false, tab.data());
+  for (long b = 0; b < B; ++b) Ph::init2_body(P, L, ws(b), io, tab.data());
+  for (int k = 0; k < L.N; ++k) for (long b = 0; b < B; ++b) Ph::der_body(P, L, ws(b), io, k, true, tab.data());
+  std::vector<int> retry, slow;
+  const Grp<1> g1(0);
+  while (n_act[sweep & 1] > 0) {
+    const int in = sweep & 1, out = in ^ 1;
+    retry.clear(); slow.clear();
+    for (int e = 0; e < n_act[in]; ++e) {                                   // pre
+      const int b = act[in][e];
+      if (Ph::pre_body(P, L, ws(b), io, b, tab.data(), g1, 0)) act[out][n_act[out]++] = b;
+    }
+    for (int e = 0; e < n_act[out]; ++e)                                    // factor
+      if (!Ph::factor_body(P, L, ws(act[out][e]), io, tab.data())) retry.push_back(act[out][e]);
+    for (int b : retry) Ph::retry_body(P, L, ws(b), io, b, tab.data(), 0);  // retry
+    for (int e = 0; e < n_act[out]; ++e)                                    // post
+      if (Ph::running(L, ws(act[out][e]))) Ph::post_body(P, L, ws(act[out][e]), io, tab.data(), g1);
+    for (int k = 0; k < L.N; ++k)                                           // trial
+      for (int e = 0; e < n_act[out]; ++e)
+        if (Ph::running(L, ws(act[out][e]))) Ph::trial_body(P, L, ws(act[out][e]), io, k, tab.data());
+    for (int e = 0; e < n_act[out]; ++e) {                                  // accept
+      const int b = act[out][e];
+      if (Ph::running(L, ws(b)) && !Ph::accept_body(P, L, ws(b), io, tab.data(), g1)) slow.push_back(b);
+    }
+    for (int b : slow) Ph::slow_body(P, L, ws(b), io, b, tab.data(), g1, 0);   // slow
+    for (int k = 0; k < L.N; ++k)                                           // der
+      for (int e = 0; e < n_act[out]; ++e) {
+        const int b = act[out][e];
+        if (Ph::running(L, ws(b))) Ph::der_body(P, L, ws(b), io, k, true, tab.data());
+      }
+    n_act[in] = 0;
+    ++sweep;
+  }
+  if (sweeps_out) *sweeps_out = sweep;
   return 0;
 }
 
@@ -83,6 +139,16 @@ int hs_solve(const mpcv_spec* s, const double* x0, const double* lbx, const doub
     HS_DISPATCH(s, 1, CALL)
 #undef CALL
   }
+}
+
+int hs_solve_phased(const mpcv_spec* s, const double* x0, const double* lbx, const double* ubx, const double* p,
+                    double* x, double* f, double* g, double* lam_g, double* lam_x, int* status, int* iters, long B,
+                    int* sweeps) {
+  SolveIO io{x0, lbx, ubx, p, x, f, g, lam_g, lam_x, status, iters, nullptr};
+  if (s->shooting == MPCV_SHOOTING_SINGLE) return -22;
+#define CALL(M) hs_solve_phased_t<M>(s, io, B, sweeps)
+  HS_DISPATCH(s, 1, CALL)
+#undef CALL
 }
 
 int hs_closed_loop(const mpcv_spec* s, const double* x_init, const double* pglob, const double* ptraj,

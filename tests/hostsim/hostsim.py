@@ -13,7 +13,8 @@ _LIB = None
 def build():
     so = os.path.join(_HERE, "libhostsim.so")
     deps = [os.path.join(_HERE, "hostsim.cpp")] + [
-        os.path.join(_CSRC, f) for f in ("mpcv_models.cuh", "mpcv_ipm.cuh", "mpcv_driver.cuh", "mpcv_params.h")]
+        os.path.join(_CSRC, f) for f in ("mpcv_models.cuh", "mpcv_ipm.cuh", "mpcv_driver.cuh", "mpcv_phase.cuh",
+                                         "mpcv_params.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
                                "-ffp-contract=off", "-x", "c++", os.path.join(_HERE, "hostsim.cpp"), "-o", so])
@@ -35,7 +36,10 @@ def _f64(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
 
 
-def solve(spec, x0, lbx, ubx, p):
+def solve(spec, x0, lbx, ubx, p, phased=False, libpath=None):
+    """phased=True replays the phase-kernel pipeline's schedule (mpcv_phase.cuh) instead of the
+    one-kernel solve; libpath loads another build of the harness (A/B checks of refactors)."""
+    L = lib() if libpath is None else C.CDLL(libpath)
     p = _f64(p)
     if p.ndim == 1:
         p = p[None, :]
@@ -46,10 +50,17 @@ def solve(spec, x0, lbx, ubx, p):
     ubx = _f64(np.broadcast_to(np.inf if ubx is None else ubx, (n,)))
     x = np.empty((B, n)); f = np.empty(B); g = np.empty((B, ng)); lam_g = np.empty((B, ng)); lam_x = np.empty((B, n))
     status = np.empty(B, np.int32); iters = np.empty(B, np.int32)
-    rc = lib().hs_solve(C.byref(spec), _p(x0), _p(lbx), _p(ubx), _p(p), _p(x), _p(f), _p(g), _p(lam_g), _p(lam_x),
-                        _p(status, C.c_int32), _p(iters, C.c_int32), C.c_long(B))
+    args = (C.byref(spec), _p(x0), _p(lbx), _p(ubx), _p(p), _p(x), _p(f), _p(g), _p(lam_g), _p(lam_x),
+            _p(status, C.c_int32), _p(iters, C.c_int32), C.c_long(B))
+    out = {"x": x, "f": f, "g": g, "lam_g": lam_g, "lam_x": lam_x, "status": status, "iters": iters}
+    if phased:
+        sweeps = C.c_int(0)
+        rc = L.hs_solve_phased(*args, C.byref(sweeps))
+        out["sweeps"] = sweeps.value
+    else:
+        rc = L.hs_solve(*args)
     assert rc == 0, rc
-    return {"x": x, "f": f, "g": g, "lam_g": lam_g, "lam_x": lam_x, "status": status, "iters": iters}
+    return out
 
 
 def stage_derivs(spec, z, pstage, lam):

@@ -147,6 +147,64 @@ def test_unicycle_ms_warp_layout_equals_thread_layout(mv):
     assert np.abs(out[0][0]["x"] - out[1][0]["x"]).max() <= 1e-7
 
 
+@pytest.mark.parametrize("hostloop", [False, True])
+def test_phased_layout_equals_thread_layout(mv, hostloop, monkeypatch):
+    """The phase-kernel pipeline (one CUDA graph with a conditional WHILE node, or the host-driven
+    loop over the same kernels) runs the same phase functions as the one-kernel thread layout."""
+    if hostloop:
+        monkeypatch.setenv("MPCV_PHASE_HOSTLOOP", "1")
+    x0s, p = common.unicycle_batch(3000, seed=21)
+    out = []
+    for layout in (S.LAYOUT_THREAD, S.LAYOUT_PHASED):
+        solver = _solver(mv, problems.unicycle_multiple_shooting(), layout=layout)
+        sp = solver.spec
+        lbx, ubx = problems.unicycle_bounds(sp, x_box=20.0)
+        sol = solver(x0=problems.cold_start(sp, x0s), lbx=lbx, ubx=ubx, p=p)
+        st = solver.stats()
+        assert st["success"]
+        out.append((sol, st["iter_count"]))
+        if layout == S.LAYOUT_PHASED:
+            sweeps = solver.phase_sweeps()
+            assert sweeps >= st["iter_count"].max() + 1 and (hostloop or sweeps == st["iter_count"].max() + 1)
+            # a second call on the same handle (graph re-launch) and a smaller batch (same graph, early exits)
+            sol2 = solver(x0=problems.cold_start(sp, x0s), lbx=lbx, ubx=ubx, p=p)
+            assert np.array_equal(sol2["x"], sol["x"]) and np.array_equal(sol2["f"], sol["f"])
+            sol3 = solver(x0=problems.cold_start(sp, x0s[:77]), lbx=lbx, ubx=ubx, p=p[:77])
+            assert np.array_equal(sol3["x"], sol["x"][:77])
+    assert np.mean(out[0][1] == out[1][1]) >= 0.99
+    same = out[0][1] == out[1][1]
+    assert np.abs(out[0][0]["x"][same] - out[1][0]["x"][same]).max() <= 1e-9
+    assert np.abs(out[0][0]["x"] - out[1][0]["x"]).max() <= 1e-5
+    for k in ("g", "lam_g", "lam_x"):
+        assert np.abs(out[0][0][k][same] - out[1][0][k][same]).max() <= 1e-6 * (1 + np.abs(out[0][0][k]).max())
+
+
+def test_phased_solve_is_deterministic_across_replicas(mv):
+    """Replicas of the same problems spread over one batch (and over repeated calls) must come out
+    bit-identical: every lane-group / list position / launch is interchangeable.  The all-zeros guess far
+    from the target exercises inertia retries, backtracking and second-order corrections."""
+    solver = _solver(mv, problems.unicycle_multiple_shooting())
+    sp = solver.spec
+    lbx, ubx = problems.unicycle_bounds(sp)
+    x0s, p8 = common.unicycle_batch(8, seed=77)
+    p8[0] = [0, 0, 0, 10, 10, 0]
+    reps = 517
+    p = np.tile(p8, (reps, 1))
+    ref = None
+    for trial in range(4):
+        sol = solver(x0=np.zeros((8 * reps, sp.n_var)), lbx=lbx, ubx=ubx, p=p)
+        it = solver.stats()["iter_count"].reshape(reps, 8)
+        x = sol["x"].reshape(reps, 8, -1)
+        f = sol["f"].reshape(reps, 8)
+        assert np.array_equal(it, np.tile(it[0], (reps, 1))), np.argwhere(it != it[0])[:5]
+        assert np.array_equal(x, np.tile(x[0], (reps, 1, 1)))
+        assert np.array_equal(f, np.tile(f[0], (reps, 1)))
+        if ref is None:
+            ref = (it[0].copy(), x[0].copy())
+        assert np.array_equal(ref[0], it[0]) and np.array_equal(ref[1], x[0])
+    assert ref[0][0] == 18          # the scripts' first solve (see test_unicycle_ms_first_solve_known_answer)
+
+
 def test_single_shooting_batch_vs_oracle_and_ms_equivalence(mv):
     x0s, p = common.unicycle_batch(512, seed=11)
     ss = _solver(mv, problems.unicycle_single_shooting_rk4())

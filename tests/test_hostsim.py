@@ -92,3 +92,41 @@ def test_pendulum_move_blocking_closed_loop():
     assert b["status"][0] == 0
     assert np.abs(b["controls"][0, :nst, 0] - g[:nst, 4]).max() <= 1e-5
     assert np.abs(b["states"][0, :nst + 1, :4] - g[:nst + 1, :4]).max() <= 1e-4
+
+
+def _same(a, b):
+    return all(np.array_equal(a[k], b[k]) for k in ("x", "f", "g", "lam_g", "lam_x", "status", "iters"))
+
+
+def test_phase_pipeline_schedule_is_bit_identical_to_one_kernel_solve():
+    """mpcv_phase.cuh runs the SAME phase functions as Ipm::solve(), one batch-wide launch per phase with
+    the scalar state parked in the workspace, per-stage costs reduced in the per-problem phase and an
+    active list compacted every sweep.  Replayed on the CPU the results must not differ in one bit."""
+    sp = S.unicycle_multiple_shooting()
+    x0s, p = common.unicycle_batch(200)
+    lbx, ubx = problems.unicycle_bounds(sp, x_box=20.0)
+    w0 = problems.cold_start(sp, x0s)
+    a, b = H.solve(sp, w0, lbx, ubx, p), H.solve(sp, w0, lbx, ubx, p, phased=True)
+    assert np.all(a["status"] == 0) and _same(a, b)
+    assert b["sweeps"] == a["iters"].max() + 1          # one extra sweep detects the last convergence
+    # the script's w0 = 0 far from the target: backtracking, second-order corrections, failures
+    x0s, p = common.unicycle_batch(100, seed=77)
+    lbx, ubx = problems.unicycle_bounds(sp)
+    a, b = H.solve(sp, None, lbx, ubx, p), H.solve(sp, None, lbx, ubx, p, phased=True)
+    assert _same(a, b)
+    # linear model with input-increment cost and move blocking (fixed variables, chain-rule folding)
+    sp3, lbx3, ubx3, pglob3, _, _ = common.pendulum_setup(N=50, ntu=5)
+    x0, pp = common.pendulum_batch(sp3, pglob3, 8)
+    w = problems.cold_start(sp3, x0)
+    assert _same(H.solve(sp3, w, lbx3, ubx3, pp), H.solve(sp3, w, lbx3, ubx3, pp, phased=True))
+    # per-stage reference parameters
+    spt = S.unicycle_tracking(N=20, T=0.05, M=1)
+    rng = np.random.default_rng(4)
+    B = 32
+    t = np.arange(spt.N) * spt.T
+    x0 = np.stack([1 + rng.normal(size=B) * 0.1, rng.normal(size=B) * 0.1, math.pi / 2 + rng.normal(size=B) * 0.1], 1)
+    stage = np.stack([np.cos(0.1 * t), np.sin(0.1 * t), math.pi / 2 + 0.1 * t, np.ones_like(t) * 0.1, np.ones_like(t) * 0.1], 1)
+    pt = np.concatenate([x0, np.tile(stage.ravel(), (B, 1))], 1)
+    lbt, ubt = problems.control_box(spt, (-1, -math.pi / 4), (1, math.pi / 4), (-20, -2, -np.inf), (20, 2, np.inf))
+    wt = problems.cold_start(spt, x0)
+    assert _same(H.solve(spt, wt, lbt, ubt, pt), H.solve(spt, wt, lbt, ubt, pt, phased=True))
