@@ -17,9 +17,10 @@
 // problem b at slab[(b/32)*32*total + i*32 + b%32]); the scalar state of a solve (mu, tau, filter, ...) is parked in
 // ws[L.st ..] between launches.
 //
-// One interior-point iteration = pre -> factor -> retry -> post -> trial -> accept -> slow -> der -> flip:
+// One interior-point iteration = pre -> repack -> factor -> retry -> post -> trial -> accept -> slow -> der -> flip:
 //   pre     8 lanes / problem     error measures, convergence test (exports finished problems), barrier
 //                                 update, Sigma / barrier gradient; ordered compaction of the active list
+//   repack  thread per problem    (when a quarter of the slots have emptied) dense copy of the survivors
 //   factor  thread per problem    Riccati factorisation with delta_w = 0 + vector recursions
 //   retry   thread per problem    IPOPT's delta_w schedule, only over the problems with wrong inertia
 //   post    8 lanes / problem     fraction-to-the-boundary step, merit-function terms
@@ -50,7 +51,13 @@ struct PhaseCtrl {
   int n_retry;    // problems whose first factorisation had the wrong inertia (this sweep)
   int n_slow;     // problems whose full step was rejected by the filter (this sweep)
   int sweeps_cum; // sweeps since the handle was created (launch accounting)
+  int cur;        // which of the two slabs holds the workspaces
+  int slots;      // workspace slots in use since the last repack (the lists hold slot indices)
+  int repacks;    // repacks of this call
+  int pad;
 };
+constexpr int kRepackMin = 512;     // do not bother to repack fewer survivors than this
+constexpr int kWideBelow = 4096;    // below this many active problems the lane-group kernels use 32 lanes
 
 template <class Model, class WS, int LANES = 1>
 struct Phase {
@@ -68,6 +75,7 @@ struct Phase {
     ipm.start();
     ipm.save_state(kRunning);
     ws[L.st + 14] = long_as_double(t0);
+    ws[L.st + 15] = (double)b;          // the problem's index in the caller's batch (slots move on repack)
   }
 
   // derivative sweep, one shooting interval                                   (thread per interval)
@@ -176,7 +184,8 @@ struct Phase {
   }
 
   template <class I>
-  MPCV_HD static void finish(I& ipm, int status, const SolveIO& io, long b, long long now) {
+  MPCV_HD static void finish(I& ipm, int status, const SolveIO& io, long /*slot*/, long long now) {
+    const long b = (long)ipm.ws[ipm.L.st + 15];
     const SolveInfo info = ipm.finish(status);
     export_solution(ipm, info, io, b);
     ipm.save_state(status);
@@ -223,7 +232,7 @@ __device__ __forceinline__ const BndEntry* ph_bounds_table(const Params& P, cons
 struct PhaseArgs {
   Params P;
   Layout L;
-  double* slab;
+  double* slab[2];     // ping-pong: survivors are repacked densely from one into the other
   int* act[2];
   int* retry;          // problems needing inertia-correction retries this sweep
   int* slow;           // problems needing the slow line-search path this sweep
@@ -245,12 +254,13 @@ constexpr int kGroupLanes = 8;
 
 template <class Model>
 __global__ void __launch_bounds__(kPhaseThreads) ph_init_kernel(const __grid_constant__ PhaseArgs a) {
+  double* const slab = a.slab[a.ctrl->cur];
   const SolveIO io = *a.io;
   const BndEntry* tab = ph_bounds_table<Model>(a.P, a.L, io);
   const long B = a.ctrl->B;
   for (long b = (long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long)gridDim.x * blockDim.x) {
     a.act[0][b] = (int)b;
-    Phase<Model, WsStrided>::init_body(a.P, a.L, WsStrided::of(a.slab, a.L.total, b), io, b, tab,
+    Phase<Model, WsStrided>::init_body(a.P, a.L, WsStrided::of(slab, a.L.total, b), io, b, tab,
                                        io.ns ? ph_globaltimer() : 0);
   }
 }
@@ -258,23 +268,25 @@ __global__ void __launch_bounds__(kPhaseThreads) ph_init_kernel(const __grid_con
 // first derivative sweeps (all problems): thread per (problem, interval)
 template <class Model>
 __global__ void __launch_bounds__(kPhaseThreads) ph_der0_kernel(const __grid_constant__ PhaseArgs a, int want_hess) {
+  double* const slab = a.slab[a.ctrl->cur];
   const SolveIO io = *a.io;
   const BndEntry* tab = ph_bounds_table<Model>(a.P, a.L, io);
   const long B = a.ctrl->B, items = B * a.L.N;
   for (long it = (long)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (long)gridDim.x * blockDim.x) {
     const long b = it % B;
     const int k = (int)(it / B);
-    Phase<Model, WsStrided>::der_body(a.P, a.L, WsStrided::of(a.slab, a.L.total, b), io, k, want_hess != 0, tab);
+    Phase<Model, WsStrided>::der_body(a.P, a.L, WsStrided::of(slab, a.L.total, b), io, k, want_hess != 0, tab);
   }
 }
 
 template <class Model>
 __global__ void __launch_bounds__(kPhaseThreads) ph_init2_kernel(const __grid_constant__ PhaseArgs a) {
+  double* const slab = a.slab[a.ctrl->cur];
   const SolveIO io = *a.io;
   const BndEntry* tab = ph_bounds_table<Model>(a.P, a.L, io);
   const long B = a.ctrl->B;
   for (long b = (long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long)gridDim.x * blockDim.x)
-    Phase<Model, WsStrided>::init2_body(a.P, a.L, WsStrided::of(a.slab, a.L.total, b), io, tab);
+    Phase<Model, WsStrided>::init2_body(a.P, a.L, WsStrided::of(slab, a.L.total, b), io, tab);
 }
 
 // warp-aggregated append of the flagged lanes' problem indices to a list (order kept within the warp)
@@ -289,45 +301,97 @@ __device__ __forceinline__ void ph_append(bool flag, int b, int* list, int* coun
   }
 }
 
-// pre: one warp per problem.  The surviving problems of a CTA pass are appended to the output list as
+// pre: LANES lanes per problem.  The surviving problems of a CTA pass are appended to the output list as
 // ONE contiguous, order-preserving run, so the thread-per-problem Riccati kernels that follow keep
 // reading neighbouring problems in neighbouring lanes (whole 32-byte sectors of the blocked slab).
-template <class Model>
-__global__ void __launch_bounds__(kWarpPhaseThreads, 3) ph_pre_kernel(const __grid_constant__ PhaseArgs a) {
-  constexpr int GPB = kWarpPhaseThreads / kGroupLanes;   // problems per CTA pass (32)
+template <class Model, int LANES>
+__device__ __forceinline__ void ph_pre_run(const PhaseArgs& a, double* slab, const SolveIO& io, const BndEntry* tab,
+                                           int in, int out, int n_in, int* keep_s, int* b_s, int* base_s) {
+  constexpr int GPB = kWarpPhaseThreads / LANES;   // problems per CTA pass
   static_assert(GPB <= 32, "one ballot covers the CTA's problems");
-  __shared__ int keep_s[GPB], b_s[GPB], base_s;
-  const int in = a.ctrl->sweep & 1, out = in ^ 1;
-  const int n_in = a.ctrl->n_act[in];
-  const int wpb = GPB, warp = threadIdx.x / kGroupLanes, lane = threadIdx.x & 31;
-  const Grp<kGroupLanes> g(lane);
-  if ((long)blockIdx.x * wpb >= n_in) return;
-  const SolveIO io = *a.io;
-  const BndEntry* tab = ph_bounds_table<Model>(a.P, a.L, io);
-  for (long e0 = (long)blockIdx.x * wpb; e0 < n_in; e0 += (long)gridDim.x * wpb) {
-    const long e = e0 + warp;
+  const int grp = threadIdx.x / LANES, lane = threadIdx.x & 31;
+  const Grp<LANES> g(lane);
+  for (long e0 = (long)blockIdx.x * GPB; e0 < n_in; e0 += (long)gridDim.x * GPB) {
+    const long e = e0 + grp;
     bool keep = false;
     int b = 0;
     if (e < n_in) {
       b = a.act[in][e];
-      keep = Phase<Model, WsStrided, kGroupLanes>::pre_body(a.P, a.L, WsStrided::of(a.slab, a.L.total, b), io, b, tab, g,
-                                                            io.ns ? ph_globaltimer() : 0);
+      keep = Phase<Model, WsStrided, LANES>::pre_body(a.P, a.L, WsStrided::of(slab, a.L.total, b), io, b, tab, g,
+                                                      io.ns ? ph_globaltimer() : 0);
     }
-    if (g.lane == 0) { keep_s[warp] = keep ? 1 : 0; b_s[warp] = b; }
+    if (g.lane == 0) { keep_s[grp] = keep ? 1 : 0; b_s[grp] = b; }
     __syncthreads();
     if (threadIdx.x < 32) {
-      const bool k = lane < wpb && keep_s[lane] != 0;
+      const bool k = lane < GPB && keep_s[lane] != 0;
       const unsigned m = __ballot_sync(0xffffffffu, k);
-      if (lane == 0) base_s = m ? atomicAdd(&a.ctrl->n_act[out], __popc(m)) : 0;
+      if (lane == 0) *base_s = m ? atomicAdd(&a.ctrl->n_act[out], __popc(m)) : 0;
       __syncwarp();
-      if (k) a.act[out][base_s + __popc(m & ((1u << lane) - 1u))] = b_s[lane];
+      if (k) a.act[out][*base_s + __popc(m & ((1u << lane) - 1u))] = b_s[lane];
     }
     __syncthreads();
   }
 }
 
 template <class Model>
+__global__ void __launch_bounds__(kWarpPhaseThreads, 3) ph_pre_kernel(const __grid_constant__ PhaseArgs a) {
+  double* const slab = a.slab[a.ctrl->cur];
+  __shared__ int keep_s[32], b_s[32], base_s;
+  const int in = a.ctrl->sweep & 1, out = in ^ 1;
+  const int n_in = a.ctrl->n_act[in];
+  const bool wide = n_in < kWideBelow;
+  if ((long)blockIdx.x * (kWarpPhaseThreads / (wide ? 32 : kGroupLanes)) >= n_in) return;
+  const SolveIO io = *a.io;
+  const BndEntry* tab = ph_bounds_table<Model>(a.P, a.L, io);
+  if (wide) ph_pre_run<Model, 32>(a, slab, io, tab, in, out, n_in, keep_s, b_s, &base_s);
+  else ph_pre_run<Model, kGroupLanes>(a, slab, io, tab, in, out, n_in, keep_s, b_s, &base_s);
+}
+
+// Repack: once a quarter of the slots have emptied, the survivors' workspaces are copied densely into the
+// other slab (slot e <- slot list[e]) and the list becomes the identity.  Between repacks at least 75% of
+// every 32-byte sector a warp touches is live data; without it the survivors end up one per sector and
+// every phase moves 4x the bytes it uses.
+__device__ __forceinline__ bool ph_repack_wanted(const PhaseCtrl* c, int n) {
+  return n >= kRepackMin && (long)n * 4 <= (long)c->slots * 3;
+}
+
+template <class Model>
+__global__ void __launch_bounds__(kPhaseThreads) ph_repack_kernel(const __grid_constant__ PhaseArgs a) {
+  const int out = (a.ctrl->sweep & 1) ^ 1;
+  const int n = a.ctrl->n_act[out];
+  if (!ph_repack_wanted(a.ctrl, n)) return;
+  const double* src = a.slab[a.ctrl->cur];
+  double* dst = a.slab[a.ctrl->cur ^ 1];
+  const int total = a.L.total;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) {
+    const int sl = a.act[out][e];
+    const double* ps = src + (long)(sl >> 5) * ((long)total * 32) + (sl & 31);
+    double* pd = dst + (e >> 5) * ((long)total * 32) + (e & 31);
+    int i = 0;
+    for (; i + 8 <= total; i += 8) {
+      double v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = ps[(long)(i + j) * 32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) pd[(long)(i + j) * 32] = v[j];
+    }
+    for (; i < total; ++i) pd[(long)i * 32] = ps[(long)i * 32];
+    a.act[out][e] = (int)e;
+  }
+}
+
+static __global__ void ph_repack_commit_kernel(PhaseCtrl* ctrl) {
+  const int out = (ctrl->sweep & 1) ^ 1;
+  const int n = ctrl->n_act[out];
+  if (!ph_repack_wanted(ctrl, n)) return;
+  ctrl->cur ^= 1;
+  ctrl->slots = n;
+  ctrl->repacks += 1;
+}
+
+template <class Model>
 __global__ void __launch_bounds__(kPhaseThreads, 4) ph_factor_kernel(const __grid_constant__ PhaseArgs a) {
+  double* const slab = a.slab[a.ctrl->cur];
   const int out = (a.ctrl->sweep & 1) ^ 1;
   const int n = a.ctrl->n_act[out];
   if ((long)blockIdx.x * blockDim.x >= n) return;
@@ -339,7 +403,7 @@ __global__ void __launch_bounds__(kPhaseThreads, 4) ph_factor_kernel(const __gri
     int b = 0;
     if (e < n) {
       b = a.act[out][e];
-      retry = !Phase<Model, WsStrided>::factor_body(a.P, a.L, WsStrided::of(a.slab, a.L.total, b), io, tab);
+      retry = !Phase<Model, WsStrided>::factor_body(a.P, a.L, WsStrided::of(slab, a.L.total, b), io, tab);
     }
     ph_append(retry, b, a.retry, &a.ctrl->n_retry);
   }
@@ -347,36 +411,47 @@ __global__ void __launch_bounds__(kPhaseThreads, 4) ph_factor_kernel(const __gri
 
 template <class Model>
 __global__ void __launch_bounds__(kPhaseThreads, 4) ph_retry_kernel(const __grid_constant__ PhaseArgs a) {
+  double* const slab = a.slab[a.ctrl->cur];
   const int n = a.ctrl->n_retry;
   if ((long)blockIdx.x * blockDim.x >= n) return;
   const SolveIO io = *a.io;
   const BndEntry* tab = ph_bounds_table<Model>(a.P, a.L, io);
   for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) {
     const int b = a.retry[e];
-    Phase<Model, WsStrided>::retry_body(a.P, a.L, WsStrided::of(a.slab, a.L.total, b), io, b, tab,
+    Phase<Model, WsStrided>::retry_body(a.P, a.L, WsStrided::of(slab, a.L.total, b), io, b, tab,
                                         io.ns ? ph_globaltimer() : 0);
+  }
+}
+
+template <class Model, int LANES>
+__device__ __forceinline__ void ph_post_run(const PhaseArgs& a, double* slab, const SolveIO& io, const BndEntry* tab,
+                                            int out, int n) {
+  const int gpb = blockDim.x / LANES, grp = threadIdx.x / LANES;
+  const Grp<LANES> g(threadIdx.x & 31);
+  for (long e = (long)blockIdx.x * gpb + grp; e < n; e += (long)gridDim.x * gpb) {
+    const int b = a.act[out][e];
+    const WsStrided ws = WsStrided::of(slab, a.L.total, b);
+    if (!Phase<Model, WsStrided>::running(a.L, ws)) continue;     // retries exhausted: already exported
+    Phase<Model, WsStrided, LANES>::post_body(a.P, a.L, ws, io, tab, g);
   }
 }
 
 template <class Model>
 __global__ void __launch_bounds__(kWarpPhaseThreads, 3) ph_post_kernel(const __grid_constant__ PhaseArgs a) {
+  double* const slab = a.slab[a.ctrl->cur];
   const int out = (a.ctrl->sweep & 1) ^ 1;
   const int n = a.ctrl->n_act[out];
-  const int wpb = blockDim.x / kGroupLanes, warp = threadIdx.x / kGroupLanes;
-  const Grp<kGroupLanes> g(threadIdx.x & 31);
-  if ((long)blockIdx.x * wpb >= n) return;
+  const bool wide = n < kWideBelow;
+  if ((long)blockIdx.x * (kWarpPhaseThreads / (wide ? 32 : kGroupLanes)) >= n) return;
   const SolveIO io = *a.io;
   const BndEntry* tab = ph_bounds_table<Model>(a.P, a.L, io);
-  for (long e = (long)blockIdx.x * wpb + warp; e < n; e += (long)gridDim.x * wpb) {
-    const int b = a.act[out][e];
-    const WsStrided ws = WsStrided::of(a.slab, a.L.total, b);
-    if (!Phase<Model, WsStrided>::running(a.L, ws)) continue;     // retries exhausted: already exported
-    Phase<Model, WsStrided, kGroupLanes>::post_body(a.P, a.L, ws, io, tab, g);
-  }
+  if (wide) ph_post_run<Model, 32>(a, slab, io, tab, out, n);
+  else ph_post_run<Model, kGroupLanes>(a, slab, io, tab, out, n);
 }
 
 template <class Model>
 __global__ void __launch_bounds__(kPhaseThreads) ph_trial_kernel(const __grid_constant__ PhaseArgs a) {
+  double* const slab = a.slab[a.ctrl->cur];
   const int out = (a.ctrl->sweep & 1) ^ 1;
   const long n = a.ctrl->n_act[out], items = n * a.L.N;
   if ((long)blockIdx.x * blockDim.x >= items) return;
@@ -385,32 +460,42 @@ __global__ void __launch_bounds__(kPhaseThreads) ph_trial_kernel(const __grid_co
   for (long it = (long)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (long)gridDim.x * blockDim.x) {
     const int b = a.act[out][it % n];
     const int k = (int)(it / n);
-    const WsStrided ws = WsStrided::of(a.slab, a.L.total, b);
+    const WsStrided ws = WsStrided::of(slab, a.L.total, b);
     if (!Phase<Model, WsStrided>::running(a.L, ws)) continue;
     Phase<Model, WsStrided>::trial_body(a.P, a.L, ws, io, k, tab);
   }
 }
 
-template <class Model>
-__global__ void __launch_bounds__(kWarpPhaseThreads, 3) ph_accept_kernel(const __grid_constant__ PhaseArgs a) {
-  const int out = (a.ctrl->sweep & 1) ^ 1;
-  const int n = a.ctrl->n_act[out];
-  const int wpb = blockDim.x / kGroupLanes, warp = threadIdx.x / kGroupLanes;
-  const Grp<kGroupLanes> g(threadIdx.x & 31);
-  if ((long)blockIdx.x * wpb >= n) return;
-  const SolveIO io = *a.io;
-  const BndEntry* tab = ph_bounds_table<Model>(a.P, a.L, io);
-  for (long e = (long)blockIdx.x * wpb + warp; e < n; e += (long)gridDim.x * wpb) {
+template <class Model, int LANES>
+__device__ __forceinline__ void ph_accept_run(const PhaseArgs& a, double* slab, const SolveIO& io, const BndEntry* tab,
+                                              int out, int n) {
+  const int gpb = blockDim.x / LANES, grp = threadIdx.x / LANES;
+  const Grp<LANES> g(threadIdx.x & 31);
+  for (long e = (long)blockIdx.x * gpb + grp; e < n; e += (long)gridDim.x * gpb) {
     const int b = a.act[out][e];
-    const WsStrided ws = WsStrided::of(a.slab, a.L.total, b);
+    const WsStrided ws = WsStrided::of(slab, a.L.total, b);
     if (!Phase<Model, WsStrided>::running(a.L, ws)) continue;
-    const bool ok = Phase<Model, WsStrided, kGroupLanes>::accept_body(a.P, a.L, ws, io, tab, g);
+    const bool ok = Phase<Model, WsStrided, LANES>::accept_body(a.P, a.L, ws, io, tab, g);
     if (!ok && g.lane == 0) a.slow[atomicAdd(&a.ctrl->n_slow, 1)] = b;
   }
 }
 
 template <class Model>
+__global__ void __launch_bounds__(kWarpPhaseThreads, 3) ph_accept_kernel(const __grid_constant__ PhaseArgs a) {
+  double* const slab = a.slab[a.ctrl->cur];
+  const int out = (a.ctrl->sweep & 1) ^ 1;
+  const int n = a.ctrl->n_act[out];
+  const bool wide = n < kWideBelow;
+  if ((long)blockIdx.x * (kWarpPhaseThreads / (wide ? 32 : kGroupLanes)) >= n) return;
+  const SolveIO io = *a.io;
+  const BndEntry* tab = ph_bounds_table<Model>(a.P, a.L, io);
+  if (wide) ph_accept_run<Model, 32>(a, slab, io, tab, out, n);
+  else ph_accept_run<Model, kGroupLanes>(a, slab, io, tab, out, n);
+}
+
+template <class Model>
 __global__ void __launch_bounds__(kWarpPhaseThreads) ph_slow_kernel(const __grid_constant__ PhaseArgs a) {
+  double* const slab = a.slab[a.ctrl->cur];
   const int n = a.ctrl->n_slow;
   const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((long)blockIdx.x * wpb >= n) return;
@@ -418,13 +503,14 @@ __global__ void __launch_bounds__(kWarpPhaseThreads) ph_slow_kernel(const __grid
   const BndEntry* tab = ph_bounds_table<Model>(a.P, a.L, io);
   for (long e = (long)blockIdx.x * wpb + warp; e < n; e += (long)gridDim.x * wpb) {
     const int b = a.slow[e];
-    Phase<Model, WsStrided, 32>::slow_body(a.P, a.L, WsStrided::of(a.slab, a.L.total, b), io, b, tab,
+    Phase<Model, WsStrided, 32>::slow_body(a.P, a.L, WsStrided::of(slab, a.L.total, b), io, b, tab,
                                            Grp<32>(lane), io.ns ? ph_globaltimer() : 0);
   }
 }
 
 template <class Model>
 __global__ void __launch_bounds__(kPhaseThreads) ph_der_kernel(const __grid_constant__ PhaseArgs a) {
+  double* const slab = a.slab[a.ctrl->cur];
   const int out = (a.ctrl->sweep & 1) ^ 1;
   const long n = a.ctrl->n_act[out], items = n * a.L.N;
   if ((long)blockIdx.x * blockDim.x >= items) return;
@@ -433,7 +519,7 @@ __global__ void __launch_bounds__(kPhaseThreads) ph_der_kernel(const __grid_cons
   for (long it = (long)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (long)gridDim.x * blockDim.x) {
     const int b = a.act[out][it % n];
     const int k = (int)(it / n);
-    const WsStrided ws = WsStrided::of(a.slab, a.L.total, b);
+    const WsStrided ws = WsStrided::of(slab, a.L.total, b);
     if (!Phase<Model, WsStrided>::running(a.L, ws)) continue;   // failed this sweep: nothing to refresh
     Phase<Model, WsStrided>::der_body(a.P, a.L, ws, io, k, true, tab);
   }
@@ -456,6 +542,7 @@ static __global__ void ph_begin_kernel(PhaseCtrl* ctrl, SolveIO* dst, const Solv
   ctrl->B = B;
   ctrl->n_act[0] = B; ctrl->n_act[1] = 0; ctrl->sweep = 0; ctrl->sweeps_total = 0;
   ctrl->n_retry = 0; ctrl->n_slow = 0;
+  ctrl->cur = 0; ctrl->slots = B; ctrl->repacks = 0;
 }
 #endif  // __CUDACC__
 

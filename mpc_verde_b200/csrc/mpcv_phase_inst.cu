@@ -18,6 +18,8 @@ struct mpcv_phase_state {
   int* act[2] = {nullptr, nullptr};
   int* retry = nullptr;
   int* slow = nullptr;
+  double* slab2 = nullptr;          // second workspace slab (repack target)
+  size_t slab2_doubles = 0;
   PhaseCtrl* ctrl = nullptr;
   SolveIO* d_io = nullptr;
   PhaseCtrl* h_ctrl = nullptr;      // pinned mirror (host-loop mode)
@@ -37,6 +39,7 @@ static void phase_free(mpcv_phase_state* s) {
   if (s->act[1]) cudaFree(s->act[1]);
   if (s->retry) cudaFree(s->retry);
   if (s->slow) cudaFree(s->slow);
+  if (s->slab2) cudaFree(s->slab2);
   if (s->ctrl) cudaFree(s->ctrl);
   if (s->d_io) cudaFree(s->d_io);
   if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
@@ -82,6 +85,15 @@ static int phase_ensure(mpcv_handle* h, long B) {
     CUDA_OK(cudaMalloc(&h->slab, need * sizeof(double)));
     h->slab_doubles = need;
   }
+  if (need > s->slab2_doubles) {
+    if (s->slab2) cudaFree(s->slab2);
+    s->slab2 = nullptr;
+    s->slab2_doubles = 0;
+    CUDA_OK(cudaMalloc(&s->slab2, need * sizeof(double)));
+    s->slab2_doubles = need;
+    if (s->exec) { cudaGraphExecDestroy(s->exec); s->exec = nullptr; }
+    if (s->graph) { cudaGraphDestroy(s->graph); s->graph = nullptr; }
+  }
   h->slab_stride = s->cap;
   if (s->exec && (s->graph_slab != h->slab || s->graph_stride != h->slab_stride)) {
     cudaGraphExecDestroy(s->exec); s->exec = nullptr;
@@ -94,7 +106,7 @@ template <class Model>
 static PhaseArgs phase_args(const mpcv_handle* h) {
   const mpcv_phase_state* s = h->phase;
   PhaseArgs a;
-  a.P = h->P; a.L = h->L; a.slab = h->slab;
+  a.P = h->P; a.L = h->L; a.slab[0] = h->slab; a.slab[1] = s->slab2;
   a.act[0] = s->act[0]; a.act[1] = s->act[1];
   a.retry = s->retry; a.slow = s->slow;
   a.ctrl = s->ctrl; a.io = s->d_io; a.cap = s->cap;
@@ -164,10 +176,13 @@ static int phase_build_graph(mpcv_handle* h) {
   cp.conditional.size = 1;
   CUDA_OK(cudaGraphAddNode(&n_while, g, &n_der1, 1, &cp));
   cudaGraph_t body = cp.conditional.phGraph_out[0];
-  cudaGraphNode_t b_pre, b_factor, b_retry, b_post, b_trial, b_accept, b_slow, b_der, b_flip;
+  cudaGraphNode_t b_pre, b_repack, b_commit, b_factor, b_retry, b_post, b_trial, b_accept, b_slow, b_der, b_flip;
   void* a_flip[] = {&s->ctrl, &handle, &use_handle};
   if (int rc = add_kernel(body, &b_pre, nullptr, (void*)ph_pre_kernel<Model>, gr.group, kWarpPhaseThreads, smem, a_init)) return rc;
-  if (int rc = add_kernel(body, &b_factor, &b_pre, (void*)ph_factor_kernel<Model>, gr.prob, kPhaseThreads, smem, a_init)) return rc;
+  void* a_ctrl[] = {&s->ctrl};
+  if (int rc = add_kernel(body, &b_repack, &b_pre, (void*)ph_repack_kernel<Model>, gr.prob, kPhaseThreads, 0, a_init)) return rc;
+  if (int rc = add_kernel(body, &b_commit, &b_repack, (void*)ph_repack_commit_kernel, 1, 1, 0, a_ctrl)) return rc;
+  if (int rc = add_kernel(body, &b_factor, &b_commit, (void*)ph_factor_kernel<Model>, gr.prob, kPhaseThreads, smem, a_init)) return rc;
   if (int rc = add_kernel(body, &b_retry, &b_factor, (void*)ph_retry_kernel<Model>, gr.prob, kPhaseThreads, smem, a_init)) return rc;
   if (int rc = add_kernel(body, &b_post, &b_retry, (void*)ph_post_kernel<Model>, gr.group, kWarpPhaseThreads, smem, a_init)) return rc;
   if (int rc = add_kernel(body, &b_trial, &b_post, (void*)ph_trial_kernel<Model>, gr.stage, kPhaseThreads, smem, a_init)) return rc;
@@ -202,6 +217,8 @@ static int phase_host_loop(mpcv_handle* h, cudaStream_t st) {
   for (long sweep = 0; sweep < (long)h->P.max_iter + 2; sweep += chunk) {
     for (int c = 0; c < chunk; ++c) {
       ph_pre_kernel<Model><<<gr.group, kWarpPhaseThreads, smem, st>>>(a);
+      ph_repack_kernel<Model><<<gr.prob, kPhaseThreads, 0, st>>>(a);
+      ph_repack_commit_kernel<<<1, 1, 0, st>>>(s->ctrl);
       ph_factor_kernel<Model><<<gr.prob, kPhaseThreads, smem, st>>>(a);
       ph_retry_kernel<Model><<<gr.prob, kPhaseThreads, smem, st>>>(a);
       ph_post_kernel<Model><<<gr.group, kWarpPhaseThreads, smem, st>>>(a);
@@ -210,7 +227,7 @@ static int phase_host_loop(mpcv_handle* h, cudaStream_t st) {
       ph_slow_kernel<Model><<<gr.warp, kWarpPhaseThreads, smem, st>>>(a);
       ph_der_kernel<Model><<<gr.stage, kPhaseThreads, smem, st>>>(a);
       ph_flip_kernel<<<1, 1, 0, st>>>(s->ctrl, none, 0);
-      h->launches += 9;
+      h->launches += 11;
     }
     CUDA_OK(cudaMemcpyAsync(s->h_ctrl, s->ctrl, sizeof(PhaseCtrl), cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
