@@ -9,7 +9,7 @@ import os
 from .spec import Spec
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmpcv.so")
+LIB_PATH = os.environ.get("MPCV_LIB") or os.path.join(_HERE, "libmpcv.so")   # MPCV_LIB: tuning builds
 _LIB = None
 
 _D = C.POINTER(C.c_double)

@@ -237,8 +237,34 @@ struct Ipm {
     b.hi = b.hasu ? u + P.bound_relax * fmax(1.0, fabs(u)) : INFINITY;
     return b;
   }
+  // Lane-strided loop over [0, n) in batches of UNR iterations per lane: the loads of the whole batch
+  // (ld) are issued before the first value is used (use), so a lane has UNR x more memory requests in
+  // flight.  Iterations run in ascending i per lane, exactly like the plain loop.
+#ifndef MPCV_UNR
+#define MPCV_UNR 1   /* measured on B200: batching costs more in registers than it hides in latency */
+#endif
+  static constexpr int UNR = LANES >= 32 ? (MPCV_UNR > 2 ? 2 : MPCV_UNR) : MPCV_UNR;
+  template <class LD, class USE>
+  MPCV_D void lane_loop(int n, LD ld, USE use) const {
+    for (int i0 = g.lane; i0 < n; i0 += LANES * UNR) {
+      decltype(ld(0)) v[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) { const int i = i0 + u * LANES; if (i < n) v[u] = ld(i); }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) { const int i = i0 + u * LANES; if (i < n) use(i, v[u]); }
+    }
+  }
+  struct V1 { double a; };
+  struct V2 { double a, b; };
+  struct V3 { double a, b, c; };
+  struct V4 { double a, b, c, d; };
+  struct V6 { double a, b, c, d, e, f; };
+
   MPCV_D Bnd bnd(int i) const {
     if (btab) {
+#if defined(__CUDA_ARCH__)
+      __builtin_assume(__isShared(btab));   // LDS instead of generic loads
+#endif
       const BndEntry e = btab[i];
       Bnd b;
       b.lo = e.lo; b.hi = e.hi;
@@ -497,20 +523,20 @@ struct Ipm {
   MPCV_D void trial_reduce(double alpha, int doff, double* f_out, double* theta_out, double* phi_out) const {
     double thpart = 0.0, logpart = 0.0;
     bool bad = false;
-    for (int i = NX + g.lane; i < L.m; i += LANES) thpart += fabs(ws[L.ct + i]);
+    lane_loop(L.m - NX, [&](int j) { return V1{ws[L.ct + NX + j]}; }, [&](int, const V1& v) { thpart += fabs(v.a); });
     for (int i = g.lane; i < NX; i += LANES) {
       const double r = ws[L.par + i] - (ws[L.w + ix(0, i)] + alpha * ws[doff + ix(0, i)]);
       thpart += fabs(r);
       ws[L.ct + i] = r;
     }
-    for (int i = g.lane; i < L.n; i += LANES) {
+    lane_loop(L.n, [&](int i) { return V2{ws[L.w + i], ws[doff + i]}; }, [&](int i, const V2& q) {
       const Bnd b = bnd(i);
       if (b.hasl || b.hasu) {
-        const double v = ws[L.w + i] + alpha * ws[doff + i];
+        const double v = q.a + alpha * q.b;
         if (b.hasl) { const double s = v - b.lo; if (!(s > 0.0)) bad = true; logpart += log(s); }
         if (b.hasu) { const double s = b.hi - v; if (!(s > 0.0)) bad = true; logpart += log(s); }
       }
-    }
+    });
     const double f = sum_stage_costs();
     const double lg = g.sum(logpart);
     const bool anybad = g.max(bad ? 1.0 : 0.0) > 0.0;
@@ -558,22 +584,22 @@ struct Ipm {
           }
         }
       }
-      for (int i = g.lane; i < L.m; i += LANES) {
-        prim = fmax(prim, fabs(ws[L.c + i]));
-        lsum += fabs(ws[L.lam + i]);
-      }
+      lane_loop(L.m, [&](int i) { return V2{ws[L.c + i], ws[L.lam + i]}; }, [&](int, const V2& v) {
+        prim = fmax(prim, fabs(v.a));
+        lsum += fabs(v.b);
+      });
     }
-    for (int i = g.lane; i < L.n; i += LANES) {
+    lane_loop(L.n, [&](int i) { return V3{ws[L.w + i], ws[L.zl + i], ws[L.zu + i]}; }, [&](int i, const V3& v) {
       const Bnd b = bnd(i);
       if (b.hasl) {
-        const double z = ws[L.zl + i], c = (ws[L.w + i] - b.lo) * z;
+        const double z = v.b, c = (v.a - b.lo) * z;
         cmin = fmin(cmin, c); cmax = fmax(cmax, c); zsum += fabs(z); nz += 1.0;
       }
       if (b.hasu) {
-        const double z = ws[L.zu + i], c = (b.hi - ws[L.w + i]) * z;
+        const double z = v.c, c = (b.hi - v.a) * z;
         cmin = fmin(cmin, c); cmax = fmax(cmax, c); zsum += fabs(z); nz += 1.0;
       }
-    }
+    });
     Err e;
     dual = g.max(dual); prim = g.max(prim); e.cmin = g.min(cmin); e.cmax = g.max(cmax);
     zsum = g.sum(zsum); lsum = g.sum(lsum); nz = g.sum(nz);
@@ -603,12 +629,16 @@ struct Ipm {
     *sg = s; *r = ri;
   }
   MPCV_D void prepare_barrier() const {
-    for (int i = g.lane; i < L.n; i += LANES) {
-      double sg, r;
-      sigma_r_compute(i, &sg, &r);
-      ws[L.sig + i] = sg;
-      ws[L.rb + i] = r;
-    }
+    lane_loop(L.n, [&](int i) { return V4{ws[L.grad + i], ws[L.w + i], ws[L.zl + i], ws[L.zu + i]}; },
+              [&](int i, const V4& v) {
+      const Bnd b = bnd(i);
+      double s = 0.0, ri = v.a;
+      // one reciprocal per bound serves Sigma = z / s and the barrier gradient mu / s
+      if (b.hasl) { const double inv = 1.0 / (v.b - b.lo); s += v.c * inv; ri -= mu * inv; }
+      if (b.hasu) { const double inv = 1.0 / (b.hi - v.b); s += v.d * inv; ri += mu * inv; }
+      ws[L.sig + i] = s;
+      ws[L.rb + i] = ri;
+    });
     g.sync();
   }
   MPCV_D void sigma_r(int i, double* sg, double* r) const { *sg = ws[L.sig + i]; *r = ws[L.rb + i]; }
@@ -734,21 +764,22 @@ struct Ipm {
             for (int j = 0; j < NX; ++j) G[i * NX + j] = 0.0;
           }
         }
-        // Cholesky of F in place (lower)
+        // Cholesky of F in place (lower); the diagonal holds the RECIPROCAL of the Cholesky pivot, so the
+        // triangular solves here and in riccati_solve multiply instead of divide
 #pragma unroll
         for (int j = 0; j < NU; ++j) {
           double dj = F[j * NU + j];
 #pragma unroll
           for (int l = 0; l < j; ++l) dj -= F[j * NU + l] * F[j * NU + l];
           if (!(dj > 0.0) || !(dj < INFINITY)) { ok = 0; dj = 1.0; }
-          dj = sqrt(dj);
+          dj = rsqrt_(dj);
           F[j * NU + j] = dj;
 #pragma unroll
           for (int i = j + 1; i < NU; ++i) {
             double v = F[i * NU + j];
 #pragma unroll
             for (int l = 0; l < j; ++l) v -= F[i * NU + l] * F[j * NU + l];
-            F[i * NU + j] = v / dj;
+            F[i * NU + j] = v * dj;
           }
         }
         // K = -F^{-1} G  (column by column)
@@ -761,14 +792,14 @@ struct Ipm {
             double v = -G[i * NX + c];
 #pragma unroll
             for (int l = 0; l < i; ++l) v -= F[i * NU + l] * t[l];
-            t[i] = v / F[i * NU + i];
+            t[i] = v * F[i * NU + i];
           }
 #pragma unroll
           for (int i = NU - 1; i >= 0; --i) {
             double v = t[i];
 #pragma unroll
             for (int l = i + 1; l < NU; ++l) v -= F[l * NU + i] * t[l];
-            t[i] = v / F[i * NU + i];
+            t[i] = v * F[i * NU + i];
           }
 #pragma unroll
           for (int i = 0; i < NU; ++i) K[i * NX + c] = t[i];
@@ -948,14 +979,14 @@ struct Ipm {
           double v = -gk[i];
 #pragma unroll
           for (int l = 0; l < i; ++l) v -= F[i * NU + l] * t[l];
-          t[i] = v / F[i * NU + i];
+          t[i] = v * F[i * NU + i];
         }
 #pragma unroll
         for (int i = NU - 1; i >= 0; --i) {
           double v = t[i];
 #pragma unroll
           for (int l = i + 1; l < NU; ++l) v -= F[l * NU + i] * t[l];
-          t[i] = v / F[i * NU + i];
+          t[i] = v * F[i * NU + i];
         }
 #pragma unroll
         for (int i = 0; i < NU; ++i) ws[ro + NU * NX + i] = t[i];
@@ -1135,23 +1166,35 @@ struct Ipm {
   }
   MPCV_D double ftb_primal() const {
     double a = 1.0;
-    for (int i = g.lane; i < L.n; i += LANES) {
+    lane_loop(L.n, [&](int i) { return V2{ws[L.w + i], ws[L.d + i]}; }, [&](int i, const V2& v) {
       const Bnd b = bnd(i);
-      const double di = ws[L.d + i];
-      if (b.hasl && di < 0.0) a = fmin(a, -tau * (ws[L.w + i] - b.lo) / di);
-      if (b.hasu && di > 0.0) a = fmin(a, tau * (b.hi - ws[L.w + i]) / di);
-    }
+      const double di = v.b;
+      if (b.hasl && di < 0.0) a = fmin(a, -tau * (v.a - b.lo) / di);
+      if (b.hasu && di > 0.0) a = fmin(a, tau * (b.hi - v.a) / di);
+    });
     return g.min(a);
   }
   // fraction-to-the-boundary rule for the bound multipliers.  The dual steps are parked in the (dead by
   // now) Sigma / barrier-gradient slots for the update that follows.
   MPCV_D double ftb_dual() const {
     double a = 1.0;
-    for (int i = g.lane; i < L.n; i += LANES) {
+    lane_loop(L.n, [&](int i) { return V4{ws[L.w + i], ws[L.d + i], ws[L.zl + i], ws[L.zu + i]}; },
+              [&](int i, const V4& v) {
       const Bnd b = bnd(i);
-      if (b.hasl) { const double dz = dz_l(i, b); ws[L.sig + i] = dz; if (dz < 0.0) a = fmin(a, -tau * ws[L.zl + i] / dz); }
-      if (b.hasu) { const double dz = dz_u(i, b); ws[L.rb + i] = dz; if (dz < 0.0) a = fmin(a, -tau * ws[L.zu + i] / dz); }
-    }
+      // dz = mu / s - z - (z / s) d  with one reciprocal per bound
+      if (b.hasl) {
+        const double inv = 1.0 / (v.a - b.lo), z = v.c;
+        const double dz = mu * inv - z - z * inv * v.b;
+        ws[L.sig + i] = dz;
+        if (dz < 0.0) a = fmin(a, -tau * z / dz);
+      }
+      if (b.hasu) {
+        const double inv = 1.0 / (b.hi - v.a), z = v.d;
+        const double dz = mu * inv - z + z * inv * v.b;
+        ws[L.rb + i] = dz;
+        if (dz < 0.0) a = fmin(a, -tau * z / dz);
+      }
+    });
     return g.min(a);
   }
   // z reset into [mu / (kappa_Sigma s), kappa_Sigma mu / s], kappa_Sigma = 1e10 (a safeguard that almost
@@ -1305,15 +1348,13 @@ struct Ipm {
   MPCV_D void direction_post() {
     ls_alpha_max = ftb_primal();
     double theta = 0.0, gBD = 0.0, lg = 0.0;
-    for (int i = g.lane; i < L.m; i += LANES) theta += fabs(ws[L.c + i]);
-    for (int i = g.lane; i < L.n; i += LANES) {
-      double sg, r;
-      sigma_r(i, &sg, &r);
+    lane_loop(L.m, [&](int i) { return V1{ws[L.c + i]}; }, [&](int, const V1& v) { theta += fabs(v.a); });
+    lane_loop(L.n, [&](int i) { return V3{ws[L.rb + i], ws[L.d + i], ws[L.w + i]}; }, [&](int i, const V3& v) {
       const Bnd b = bnd(i);
-      if (!b.fixed) gBD += r * ws[L.d + i];
-      if (b.hasl) lg += log(ws[L.w + i] - b.lo);
-      if (b.hasu) lg += log(b.hi - ws[L.w + i]);
-    }
+      if (!b.fixed) gBD += v.a * v.b;
+      if (b.hasl) lg += log(v.c - b.lo);
+      if (b.hasu) lg += log(b.hi - v.c);
+    });
     theta = g.sum(theta); gBD = g.sum(gBD); lg = g.sum(lg);
     ls_theta = theta;
     ls_gBD = gBD;
@@ -1369,15 +1410,17 @@ struct Ipm {
       }
     }
     const double alpha_dual = ftb_dual();
-    for (int i = g.lane; i < L.n; i += LANES) {
+    lane_loop(L.n, [&](int i) { return V6{ws[L.w + i], ws[L.d + i], ws[L.zl + i], ws[L.zu + i], ws[L.sig + i], ws[L.rb + i]}; },
+              [&](int i, const V6& v) {
       const Bnd b = bnd(i);
-      const double wi = ws[L.w + i] + alpha * ws[L.d + i];
+      const double wi = v.a + alpha * v.b;
       ws[L.w + i] = wi;
-      if (b.hasl) ws[L.zl + i] = clamp_z(ws[L.zl + i] + alpha_dual * ws[L.sig + i], wi - b.lo);
-      if (b.hasu) ws[L.zu + i] = clamp_z(ws[L.zu + i] + alpha_dual * ws[L.rb + i], b.hi - wi);
-    }
+      if (b.hasl) ws[L.zl + i] = clamp_z(v.c + alpha_dual * v.e, wi - b.lo);
+      if (b.hasu) ws[L.zu + i] = clamp_z(v.d + alpha_dual * v.f, b.hi - wi);
+    });
     if (!SINGLE)
-      for (int i = g.lane; i < L.m; i += LANES) ws[L.lam + i] += alpha * (ws[L.lamp + i] - ws[L.lam + i]);
+      lane_loop(L.m, [&](int i) { return V2{ws[L.lam + i], ws[L.lamp + i]}; },
+                [&](int i, const V2& v) { ws[L.lam + i] = v.a + alpha * (v.b - v.a); });
     g.sync();
     sync_blocked();
     ++iter;

@@ -56,6 +56,14 @@ MPCV_HD void sincos_(double a, double* s, double* c) {
 #endif
 }
 
+MPCV_HD double rsqrt_(double a) {
+#if defined(__CUDA_ARCH__)
+  return rsqrt(a);
+#else
+  return 1.0 / sqrt(a);
+#endif
+}
+
 // packed lower-triangular index of a symmetric matrix, i >= j
 MPCV_HD constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }
 

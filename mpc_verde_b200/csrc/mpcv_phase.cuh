@@ -242,11 +242,26 @@ struct PhaseArgs {
 };
 
 constexpr int kPhaseThreads = 128;       // thread-per-problem / thread-per-interval kernels
-constexpr int kWarpPhaseThreads = 256;   // lane-group kernels
+#ifndef MPCV_GROUP_THREADS
+#define MPCV_GROUP_THREADS 256
+#endif
+#ifndef MPCV_GROUP_LANES
+#define MPCV_GROUP_LANES 8
+#endif
+#ifndef MPCV_REPACK_NUM
+#define MPCV_REPACK_NUM 7   /* repack when n_active * DEN <= slots * NUM (1/2: 30.3 ms, 3/4: 28.2, 7/8: 27.6) */
+#endif
+#ifndef MPCV_REPACK_DEN
+#define MPCV_REPACK_DEN 8
+#endif
+constexpr int kWarpPhaseThreads = MPCV_GROUP_THREADS;   // lane-group kernels
 // pre / post / accept: 8 lanes per problem, the 4 problems of a warp being neighbours in the active list.
 // Scalar work (pow, filter logic, state hand-over) is then shared by 4 problems per warp instruction, and
 // a warp-load touches 8 whole sectors: the 4 neighbouring problems share each 32-byte sector of the slab.
-constexpr int kGroupLanes = 8;
+constexpr int kGroupLanes = MPCV_GROUP_LANES;
+#ifndef MPCV_GROUP_MINB
+#define MPCV_GROUP_MINB 4   /* 64 registers: measured best on B200 (2: 29.6 ms, 3: 28.2 ms, 4: 27.3 ms per batch) */
+#endif
 
 // Every phase kernel is launched with a FIXED grid (the launches are nodes of a CUDA graph) sized to
 // fill the GPU once, and strides over its work list: a sweep that has three problems left costs a few
@@ -334,7 +349,7 @@ __device__ __forceinline__ void ph_pre_run(const PhaseArgs& a, double* slab, con
 }
 
 template <class Model>
-__global__ void __launch_bounds__(kWarpPhaseThreads, 3) ph_pre_kernel(const __grid_constant__ PhaseArgs a) {
+__global__ void __launch_bounds__(kWarpPhaseThreads, MPCV_GROUP_MINB) ph_pre_kernel(const __grid_constant__ PhaseArgs a) {
   double* const slab = a.slab[a.ctrl->cur];
   __shared__ int keep_s[32], b_s[32], base_s;
   const int in = a.ctrl->sweep & 1, out = in ^ 1;
@@ -352,7 +367,7 @@ __global__ void __launch_bounds__(kWarpPhaseThreads, 3) ph_pre_kernel(const __gr
 // every 32-byte sector a warp touches is live data; without it the survivors end up one per sector and
 // every phase moves 4x the bytes it uses.
 __device__ __forceinline__ bool ph_repack_wanted(const PhaseCtrl* c, int n) {
-  return n >= kRepackMin && (long)n * 4 <= (long)c->slots * 3;
+  return n >= kRepackMin && (long)n * MPCV_REPACK_DEN <= (long)c->slots * MPCV_REPACK_NUM;
 }
 
 template <class Model>
@@ -380,18 +395,16 @@ __global__ void __launch_bounds__(kPhaseThreads) ph_repack_kernel(const __grid_c
   }
 }
 
-static __global__ void ph_repack_commit_kernel(PhaseCtrl* ctrl) {
-  const int out = (ctrl->sweep & 1) ^ 1;
-  const int n = ctrl->n_act[out];
-  if (!ph_repack_wanted(ctrl, n)) return;
-  ctrl->cur ^= 1;
-  ctrl->slots = n;
-  ctrl->repacks += 1;
+// slab index for the kernels that run after the repack of the current sweep (the decision is a pure
+// function of the control block, which does not change between `pre` and `flip`; `flip` commits it)
+__device__ __forceinline__ int ph_cur_after_repack(const PhaseCtrl* c) {
+  const int n = c->n_act[(c->sweep & 1) ^ 1];
+  return ph_repack_wanted(c, n) ? c->cur ^ 1 : c->cur;
 }
 
 template <class Model>
 __global__ void __launch_bounds__(kPhaseThreads, 4) ph_factor_kernel(const __grid_constant__ PhaseArgs a) {
-  double* const slab = a.slab[a.ctrl->cur];
+  double* const slab = a.slab[ph_cur_after_repack(a.ctrl)];
   const int out = (a.ctrl->sweep & 1) ^ 1;
   const int n = a.ctrl->n_act[out];
   if ((long)blockIdx.x * blockDim.x >= n) return;
@@ -411,7 +424,7 @@ __global__ void __launch_bounds__(kPhaseThreads, 4) ph_factor_kernel(const __gri
 
 template <class Model>
 __global__ void __launch_bounds__(kPhaseThreads, 4) ph_retry_kernel(const __grid_constant__ PhaseArgs a) {
-  double* const slab = a.slab[a.ctrl->cur];
+  double* const slab = a.slab[ph_cur_after_repack(a.ctrl)];
   const int n = a.ctrl->n_retry;
   if ((long)blockIdx.x * blockDim.x >= n) return;
   const SolveIO io = *a.io;
@@ -437,8 +450,8 @@ __device__ __forceinline__ void ph_post_run(const PhaseArgs& a, double* slab, co
 }
 
 template <class Model>
-__global__ void __launch_bounds__(kWarpPhaseThreads, 3) ph_post_kernel(const __grid_constant__ PhaseArgs a) {
-  double* const slab = a.slab[a.ctrl->cur];
+__global__ void __launch_bounds__(kWarpPhaseThreads, MPCV_GROUP_MINB) ph_post_kernel(const __grid_constant__ PhaseArgs a) {
+  double* const slab = a.slab[ph_cur_after_repack(a.ctrl)];
   const int out = (a.ctrl->sweep & 1) ^ 1;
   const int n = a.ctrl->n_act[out];
   const bool wide = n < kWideBelow;
@@ -451,7 +464,7 @@ __global__ void __launch_bounds__(kWarpPhaseThreads, 3) ph_post_kernel(const __g
 
 template <class Model>
 __global__ void __launch_bounds__(kPhaseThreads) ph_trial_kernel(const __grid_constant__ PhaseArgs a) {
-  double* const slab = a.slab[a.ctrl->cur];
+  double* const slab = a.slab[ph_cur_after_repack(a.ctrl)];
   const int out = (a.ctrl->sweep & 1) ^ 1;
   const long n = a.ctrl->n_act[out], items = n * a.L.N;
   if ((long)blockIdx.x * blockDim.x >= items) return;
@@ -481,8 +494,8 @@ __device__ __forceinline__ void ph_accept_run(const PhaseArgs& a, double* slab, 
 }
 
 template <class Model>
-__global__ void __launch_bounds__(kWarpPhaseThreads, 3) ph_accept_kernel(const __grid_constant__ PhaseArgs a) {
-  double* const slab = a.slab[a.ctrl->cur];
+__global__ void __launch_bounds__(kWarpPhaseThreads, MPCV_GROUP_MINB) ph_accept_kernel(const __grid_constant__ PhaseArgs a) {
+  double* const slab = a.slab[ph_cur_after_repack(a.ctrl)];
   const int out = (a.ctrl->sweep & 1) ^ 1;
   const int n = a.ctrl->n_act[out];
   const bool wide = n < kWideBelow;
@@ -495,7 +508,7 @@ __global__ void __launch_bounds__(kWarpPhaseThreads, 3) ph_accept_kernel(const _
 
 template <class Model>
 __global__ void __launch_bounds__(kWarpPhaseThreads) ph_slow_kernel(const __grid_constant__ PhaseArgs a) {
-  double* const slab = a.slab[a.ctrl->cur];
+  double* const slab = a.slab[ph_cur_after_repack(a.ctrl)];
   const int n = a.ctrl->n_slow;
   const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((long)blockIdx.x * wpb >= n) return;
@@ -510,7 +523,7 @@ __global__ void __launch_bounds__(kWarpPhaseThreads) ph_slow_kernel(const __grid
 
 template <class Model>
 __global__ void __launch_bounds__(kPhaseThreads) ph_der_kernel(const __grid_constant__ PhaseArgs a) {
-  double* const slab = a.slab[a.ctrl->cur];
+  double* const slab = a.slab[ph_cur_after_repack(a.ctrl)];
   const int out = (a.ctrl->sweep & 1) ^ 1;
   const long n = a.ctrl->n_act[out], items = n * a.L.N;
   if ((long)blockIdx.x * blockDim.x >= items) return;
@@ -528,6 +541,11 @@ __global__ void __launch_bounds__(kPhaseThreads) ph_der_kernel(const __grid_cons
 // end of an iteration sweep: swap the lists and tell the WHILE node whether anyone is left
 static __global__ void ph_flip_kernel(PhaseCtrl* ctrl, cudaGraphConditionalHandle handle, int use_handle) {
   const int in = ctrl->sweep & 1, out = in ^ 1;
+  if (ph_repack_wanted(ctrl, ctrl->n_act[out])) {      // commit this sweep's repack
+    ctrl->cur ^= 1;
+    ctrl->slots = ctrl->n_act[out];
+    ctrl->repacks += 1;
+  }
   ctrl->n_act[in] = 0;
   ctrl->n_retry = 0;
   ctrl->n_slow = 0;
