@@ -195,6 +195,15 @@ static int ensure_staging(mpcv_handle* h, size_t bytes) {
   return 0;
 }
 
+// page-locked host memory (cudaHostAlloc / cudaHostRegister / torch pin_memory) can be the source or
+// the destination of an asynchronous copy directly; pageable memory goes through the pinned staging block
+static bool is_pinned_host(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
 int mpcv_solve_host(mpcv_handle* h, const double* x0, const double* lbx, const double* ubx, const double* p,
                     double* x, double* f, double* g, double* lam_g, double* lam_x, int32_t* status,
                     int32_t* iters, int64_t B) {
@@ -210,26 +219,34 @@ int mpcv_solve_host(mpcv_handle* h, const double* x0, const double* lbx, const d
   if (int rc = ensure_staging(h, total)) return rc;
   char* hp = (char*)h->hpin;
   char* dp = (char*)h->dstage;
-  if (x0) std::memcpy(hp + o_x0, x0, B * n * 8);
-  std::memcpy(hp + o_lb, lbx, n * 8);
-  std::memcpy(hp + o_ub, ubx, n * 8);
-  std::memcpy(hp + o_p, p, B * np * 8);
   cudaStream_t st = h->own_stream;
-  CUDA_OK(cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, st));
+  struct Xfer { const void* user; size_t off, bytes; };
+  const Xfer ins[] = {{x0, o_x0, x0 ? (size_t)B * n * 8 : 0}, {lbx, o_lb, n * 8}, {ubx, o_ub, n * 8}, {p, o_p, (size_t)B * np * 8}};
+  for (const Xfer& t : ins) {
+    if (!t.user || t.bytes == 0) continue;
+    const void* src = t.user;
+    if (!is_pinned_host(t.user)) { std::memcpy(hp + t.off, t.user, t.bytes); src = hp + t.off; }
+    CUDA_OK(cudaMemcpyAsync(dp + t.off, src, t.bytes, cudaMemcpyHostToDevice, st));
+  }
   int rc = mpcv_solve(h, x0 ? (const double*)(dp + o_x0) : nullptr, (const double*)(dp + o_lb), (const double*)(dp + o_ub),
                       (const double*)(dp + o_p), (double*)(dp + o_x), (double*)(dp + o_f), g ? (double*)(dp + o_g) : nullptr,
                       lam_g ? (double*)(dp + o_lg) : nullptr, lam_x ? (double*)(dp + o_lx) : nullptr,
                       (int32_t*)(dp + o_st), (int32_t*)(dp + o_it), B, st);
   if (rc) return rc;
-  CUDA_OK(cudaMemcpyAsync(hp + in_bytes, dp + in_bytes, total - in_bytes, cudaMemcpyDeviceToHost, st));
+  const Xfer outs[] = {{x, o_x, (size_t)B * n * 8}, {f, o_f, (size_t)B * 8}, {g, o_g, (size_t)B * ng * 8},
+                       {lam_g, o_lg, (size_t)B * ng * 8}, {lam_x, o_lx, (size_t)B * n * 8}, {status, o_st, (size_t)B * 4},
+                       {iters, o_it, (size_t)B * 4}};
+  bool staged[7] = {false, false, false, false, false, false, false};
+  for (int i = 0; i < 7; ++i) {
+    const Xfer& t = outs[i];
+    if (!t.user || t.bytes == 0) continue;
+    void* dst = const_cast<void*>(t.user);
+    if (!is_pinned_host(t.user)) { dst = hp + t.off; staged[i] = true; }
+    CUDA_OK(cudaMemcpyAsync(dst, dp + t.off, t.bytes, cudaMemcpyDeviceToHost, st));
+  }
   CUDA_OK(cudaStreamSynchronize(st));
-  if (x) std::memcpy(x, hp + o_x, B * n * 8);
-  if (f) std::memcpy(f, hp + o_f, B * 8);
-  if (g) std::memcpy(g, hp + o_g, B * ng * 8);
-  if (lam_g) std::memcpy(lam_g, hp + o_lg, B * ng * 8);
-  if (lam_x) std::memcpy(lam_x, hp + o_lx, B * n * 8);
-  if (status) std::memcpy(status, hp + o_st, B * 4);
-  if (iters) std::memcpy(iters, hp + o_it, B * 4);
+  for (int i = 0; i < 7; ++i)
+    if (staged[i]) std::memcpy(const_cast<void*>(outs[i].user), hp + outs[i].off, outs[i].bytes);
   return 0;
 }
 

@@ -197,20 +197,29 @@ class NlpSolver:
                                     _ptr(iters), C.c_int64(B), stream)
                 _lib.check(rc, "mpcv_solve")
         else:
-            # host buffers: one C-ABI call does H2D (pinned staging), solve, D2H
+            # host buffers: one C-ABI call does H2D, solve, D2H.  Page-locked inputs (torch pin_memory) are
+            # copied straight from the caller's memory; the results then land in page-locked arrays cached
+            # on the solver (valid until the next call), otherwise in fresh pageable arrays.
+            pinned = isinstance(p, torch.Tensor) and p.is_pinned()
             pt = np.ascontiguousarray(pt.numpy())
             x0h = None if x0t is None else np.ascontiguousarray(x0t.numpy())
             lb = np.ascontiguousarray(self._vec(lbx, n, -math.inf, "lbx", "cpu").numpy())
             ub = np.ascontiguousarray(self._vec(ubx, n, math.inf, "ubx", "cpu").numpy())
-            out = {"x": np.empty((B, n)), "f": np.empty((B,))}
-            if "g" in outputs:
-                out["g"] = np.empty((B, ng))
-            if "lam_g" in outputs:
-                out["lam_g"] = np.empty((B, ng))
-            if "lam_x" in outputs:
-                out["lam_x"] = np.empty((B, n))
-            status = np.empty((B,), np.int32)
-            iters = np.empty((B,), np.int32)
+            shapes = {"x": (B, n), "f": (B,), "g": (B, ng), "lam_g": (B, ng), "lam_x": (B, n)}
+            keys = ["x", "f"] + [k for k in ("g", "lam_g", "lam_x") if k in outputs]
+            if pinned:
+                cache = self.__dict__.setdefault("_pinned_out", {})
+                def mk(key, shape, dtype):
+                    t = cache.get((key, shape))
+                    if t is None:
+                        t = cache[(key, shape)] = torch.empty(shape, dtype=dtype).pin_memory()
+                    return t.numpy()
+                out = {k: mk(k, shapes[k], torch.float64) for k in keys}
+                status, iters = mk("status", (B,), torch.int32), mk("iters", (B,), torch.int32)
+            else:
+                out = {k: np.empty(shapes[k]) for k in keys}
+                status = np.empty((B,), np.int32)
+                iters = np.empty((B,), np.int32)
             hp = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
             with torch.cuda.device(self.device):
                 rc = lib.mpcv_solve_host(h, hp(x0h), hp(lb), hp(ub), hp(pt), hp(out["x"]), hp(out["f"]),
