@@ -687,9 +687,20 @@ struct Ipm {
     }
   }
 
-  MPCV_DN bool riccati_factor(double dw, bool identity) {
+  MPCV_DN bool riccati_factor(double dw, bool identity) { return riccati_factor_t<false>(dw, identity, 0, -1); }
+  // FUSE: the backward VECTOR recursion of riccati_solve(rmode, coff) runs inside the factorisation loop,
+  // on the A, B, K, F, P_{k+1} already in registers (the phase pipeline's Riccati kernels are HBM-bound:
+  // a separate backward pass re-reads 30 of them per stage).  Same expressions in the same order as
+  // riccati_solve; riccati_forward() completes the step.
+  template <bool FUSE>
+  MPCV_D bool riccati_factor_t(double dw, bool identity, int rmode, int coff) {
     int ok = 1;
     if (g.lane == 0) {
+      double pv[NX];        // p_{k+1} (FUSE)
+      if (FUSE) {
+#pragma unroll
+        for (int i = 0; i < NX; ++i) { pv[i] = rvar(rmode, ix(N, i)); ws[L.pp + N * NPP + NPX + i] = pv[i]; }
+      }
       double Pm[NX * NX];   // P_{k+1}, full symmetric
 #pragma unroll
       for (int i = 0; i < NX * NX; ++i) Pm[i] = 0.0;
@@ -803,6 +814,54 @@ struct Ipm {
           }
 #pragma unroll
           for (int i = 0; i < NU; ++i) K[i * NX + c] = t[i];
+        }
+        if (FUSE) {
+          // Pd = P_{k+1} c_{k+1} + p_{k+1};  g = r_u + B' Pd;  kff = -F^{-1} g;  p_k = r_x + A' Pd + K' g
+          double Pd[NX], gk[NU], t[NU];
+#pragma unroll
+          for (int i = 0; i < NX; ++i) {
+            double v = pv[i];
+            if (coff >= 0) {
+#pragma unroll
+              for (int j = 0; j < NX; ++j) v += Pm[i * NX + j] * ws[coff + (k + 1) * NX + j];
+            }
+            Pd[i] = v;
+          }
+#pragma unroll
+          for (int i = 0; i < NU; ++i) {
+            double v = rvar(rmode, iu(k, i));
+#pragma unroll
+            for (int j = 0; j < NX; ++j) v += B[j * NU + i] * Pd[j];
+            if (bnd(iu(k, i)).fixed) v = 0.0;
+            gk[i] = v;
+          }
+#pragma unroll
+          for (int i = 0; i < NU; ++i) {
+            double v = -gk[i];
+#pragma unroll
+            for (int l = 0; l < i; ++l) v -= F[i * NU + l] * t[l];
+            t[i] = v * F[i * NU + i];
+          }
+#pragma unroll
+          for (int i = NU - 1; i >= 0; --i) {
+            double v = t[i];
+#pragma unroll
+            for (int l = i + 1; l < NU; ++l) v -= F[l * NU + i] * t[l];
+            t[i] = v * F[i * NU + i];
+          }
+#pragma unroll
+          for (int i = 0; i < NU; ++i) ws[L.ric + k * NRIC + NU * NX + i] = t[i];
+#pragma unroll
+          for (int i = 0; i < NX; ++i) {
+            double v = rvar(rmode, ix(k, i));
+#pragma unroll
+            for (int j = 0; j < NX; ++j) v += A[j * NX + i] * Pd[j];
+#pragma unroll
+            for (int j = 0; j < NU; ++j) v += K[j * NX + i] * gk[j];
+            pv[i] = v;
+          }
+#pragma unroll
+          for (int i = 0; i < NX; ++i) ws[L.pp + k * NPP + NPX + i] = pv[i];
         }
         // P_k = Qxx + A'PA + G'K  (symmetric)
 #pragma unroll
@@ -1004,7 +1063,12 @@ struct Ipm {
 #pragma unroll
         for (int i = 0; i < NX; ++i) { pv[i] = pk[i]; ws[L.pp + k * NPP + NPX + i] = pk[i]; }
       }
-      // forward sweep: dx_0 = c_0, du = K dx + kff, dx+ = A dx + B du + c+, lam+_k = P_k dx_k + p_k
+    }
+    riccati_forward(coff);
+  }
+  // forward sweep: dx_0 = c_0, du = K dx + kff, dx+ = A dx + B du + c+, lam+_k = P_k dx_k + p_k
+  MPCV_D void riccati_forward(int coff) const {
+    if (g.lane == 0) {
       double dx[NX];
 #pragma unroll
       for (int i = 0; i < NX; ++i) dx[i] = (coff >= 0) ? ws[coff + i] : 0.0;

@@ -118,8 +118,8 @@ struct Phase {
   // Returns false when the delta_w schedule has to take over.                    (thread per problem)
   MPCV_HD static bool factor_body(const Params& P, const Layout& L, WS ws, const SolveIO& io, const BndEntry* tab) {
     Ipm1 ipm(P, L, ws, Grp<1>(0), io.lbx, io.ubx, tab);
-    if (!ipm.riccati_factor(0.0, false)) return false;
-    ipm.riccati_solve(0, L.c);
+    if (!ipm.template riccati_factor_t<true>(0.0, false, 0, L.c)) return false;
+    ipm.riccati_forward(L.c);
     return true;
   }
 
@@ -133,7 +133,7 @@ struct Phase {
     while (!ok) {
       dw = ipm.next_delta_w(dw);
       if (dw > 1e20) break;
-      ok = ipm.riccati_factor(dw, false);
+      ok = ipm.template riccati_factor_t<true>(dw, false, 0, L.c);
     }
     if (!ok) {
       ipm.load_state();
@@ -141,7 +141,7 @@ struct Phase {
       return;
     }
     ws[L.st + 6] = dw;
-    ipm.riccati_solve(0, L.c);
+    ipm.riccati_forward(L.c);
   }
 
   MPCV_HD static bool running(const Layout& L, WS ws) { return (int)ws[L.st + 9] == kRunning; }
