@@ -58,6 +58,7 @@ struct mpcv_phase_vtable {
   int (*solve)(mpcv_handle*, const mpcv::SolveIO&, long, cudaStream_t);
   void (*release)(struct mpcv_phase_state*);
   int (*sweeps)(mpcv_handle*, cudaStream_t, int*, int*);
+  int (*loop)(mpcv_handle*, const mpcv::LoopIO&, long, cudaStream_t);
 };
 const mpcv_phase_vtable* mpcv_phase_vtable_of(int model);
 #define MPCV_DECLARE_MODEL(id) \

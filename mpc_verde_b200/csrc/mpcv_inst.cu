@@ -283,8 +283,10 @@ static int launch_solve(mpcv_handle* h, const SolveIO& io, long B, cudaStream_t 
 template <class Model>
 static int launch_loop(mpcv_handle* h, const LoopIO& io, long B, cudaStream_t st) {
   if (B <= 0) return 0;
-  // the closed loop runs as one kernel per call: warp layout for long horizons, thread layout otherwise
-  const bool warp = h->layout == MPCV_LAYOUT_WARP || (h->layout == MPCV_LAYOUT_PHASED && h->spec.N >= 32);
+  // phased layout: per-step prepare -> solve graph -> apply (mpcv_phase_inst.cu); otherwise the closed
+  // loop runs as one kernel per call (warp or thread layout)
+  if (h->layout == MPCV_LAYOUT_PHASED && !h->single) return mpcv_phase_vtable_of(Model::MODEL_ID)->loop(h, io, B, st);
+  const bool warp = h->layout == MPCV_LAYOUT_WARP;
   if (warp && !h->single) {
     int wpb; size_t smem;
     if (int rc = warp_config(h, &wpb, &smem)) return rc;

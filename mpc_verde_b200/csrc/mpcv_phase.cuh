@@ -562,6 +562,128 @@ static __global__ void ph_begin_kernel(PhaseCtrl* ctrl, SolveIO* dst, const Solv
   ctrl->n_retry = 0; ctrl->n_slow = 0;
   ctrl->cur = 0; ctrl->slots = B; ctrl->repacks = 0;
 }
+// ---------------------------------------------------------------------------------------
+// closed loop over the phase pipeline (the scripts' MPC loop, Casadi/multiple_shooting_casadi.py:224-298,
+// Trajectory_tracking.py:101-118): per MPC step  lp_prepare -> [solve graph] -> lp_apply, stream-ordered.
+// Same semantics as closed_loop_problem() (mpcv_driver.cuh), with the per-step solve batch-wide.
+// ---------------------------------------------------------------------------------------
+struct LoopBufs {
+  double* x0;       // [B, n]   guess of the next solve
+  double* p;        // [B, n_p] parameter vector of the next solve
+  double* x;        // [B, n]   solution of the last solve
+  double* f;        // [B]
+  double* state;    // [B, nx]  plant state
+  int* status;      // [B]
+  int* iters;       // [B]
+  int* active;      // [B]      1 while the problem's loop is running
+  int* steps;       // [B]
+  int* iters_total; // [B]
+  int* worst;       // [B]
+};
+
+template <class Model>
+__global__ void lp_begin_kernel(const Layout L, const LoopIO io, const LoopBufs lb, long B) {
+  constexpr int NX = Model::NX, NU = Model::NU, NZ = NX + NU;
+  const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double* os = io.out_states + b * (long)(io.n_steps + 1) * NX;
+  for (int i = 0; i < NX; ++i) { const double v = io.x_init[b * NX + i]; lb.state[b * NX + i] = v; os[i] = v; }
+  // first guess: X_k = state, U = 0 (repmat(state_init) of MS:213); the scripts' own w0 = 0 in reference mode
+  double* g = lb.x0 + b * L.n;
+  for (int i = 0; i < L.n; ++i) g[i] = 0.0;
+  if (io.warm_mode != MPCV_WARM_REFERENCE)
+    for (int k = 0; k <= L.N; ++k)
+      for (int i = 0; i < NX; ++i) g[k * NZ + i] = io.x_init[b * NX + i];
+  lb.active[b] = 1; lb.steps[b] = 0; lb.iters_total[b] = 0; lb.worst[b] = 0;
+}
+
+template <class Model>
+__global__ void lp_prepare_kernel(const Layout L, const LoopIO io, const LoopBufs lb, long B, int t) {
+  constexpr int NX = Model::NX, NU = Model::NU, NZ = NX + NU, NPG = Model::NPG, NPS = Model::NPS;
+  const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int np = NX + NPG + L.N * NPS;
+  double* pr = lb.p + b * np;
+  const double* st = lb.state + b * NX;
+  for (int i = 0; i < NPG; ++i) pr[NX + i] = io.pglob[b * NPG + i];
+  if (lb.active[b] && io.stop_radius > 0.0 && NPG >= NX) {
+    double d2 = 0.0;
+    for (int i = 0; i < NX; ++i) { const double e = st[i] - pr[NX + i]; d2 += e * e; }
+    if (!(sqrt(d2) > io.stop_radius)) lb.active[b] = 0;      // while norm_2(state-target) > 1e-1 (MS:226)
+  }
+  for (int i = 0; i < NX; ++i) pr[i] = st[i];
+  if (NPS > 0) {
+    // horizon window p[t..t+N) of this scenario's reference trajectory
+    const double* src = io.ptraj + (b * (long)(io.n_steps + L.N) + t) * NPS;
+    for (int i = 0; i < L.N * NPS; ++i) pr[NX + NPG + i] = src[i];
+  }
+  if (io.warm_mode == MPCV_WARM_COLD) {
+    double* g = lb.x0 + b * L.n;
+    for (int i = 0; i < L.n; ++i) g[i] = 0.0;
+    for (int k = 0; k <= L.N; ++k)
+      for (int i = 0; i < NX; ++i) g[k * NZ + i] = st[i];
+  }
+}
+
+template <class Model>
+__global__ void lp_apply_kernel(const Params P, const Layout L, const LoopIO io, const LoopBufs lb, long B, int t) {
+  constexpr int NX = Model::NX, NU = Model::NU, NZ = NX + NU, NPG = Model::NPG, NPS = Model::NPS;
+  const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B || !lb.active[b]) return;
+  const int N = L.N, np = NX + NPG + N * NPS;
+  const double* pr = lb.p + b * np;
+  const double* x = lb.x + b * L.n;       // projected solution (honor_original_bounds)
+  double* g = lb.x0 + b * L.n;
+  double* st = lb.state + b * NX;
+  double state[NX], u0[NU], xn[NX], q;
+  for (int i = 0; i < NX; ++i) state[i] = st[i];
+  for (int i = 0; i < NU; ++i) u0[i] = x[NX + i];
+  // plant step with the same discretisation: state = F(p, u0) (MS:273)
+  Model::val(P, state, u0, pr + NX, pr + NX + NPG, xn, &q);
+  // `uprev` is never updated by the reference (Inverted_pendulum/...:64): replay on request
+  if (Model::HAS_UPREV && io.warm_mode == MPCV_WARM_REFERENCE) xn[NX - 1] = io.x_init[b * NX + NX - 1];
+  double* os = io.out_states + b * (long)(io.n_steps + 1) * NX;
+  double* oc = io.out_controls + b * (long)io.n_steps * NU;
+  for (int i = 0; i < NU; ++i) oc[t * NU + i] = u0[i];
+  for (int i = 0; i < NX; ++i) { os[(t + 1) * NX + i] = xn[i]; st[i] = xn[i]; }
+  lb.steps[b] += 1;
+  lb.iters_total[b] += lb.iters[b];
+  if (lb.status[b] != 0 && lb.worst[b] == 0) lb.worst[b] = lb.status[b];
+  // next guess
+  if (io.warm_mode == MPCV_WARM_SHIFT) {
+    for (int k = 0; k < N; ++k) {
+      for (int i = 0; i < NX; ++i) g[k * NZ + i] = x[(k + 1) * NZ + i];
+      const int ks = (k + 1 < N) ? k + 1 : N - 1;            // the last control is kept
+      for (int i = 0; i < NU; ++i) g[k * NZ + NX + i] = x[ks * NZ + NX + i];
+    }
+    for (int i = 0; i < NX; ++i) g[N * NZ + i] = x[N * NZ + i];
+  } else if (io.warm_mode == MPCV_WARM_REFERENCE) {
+    int q2 = 0;   // MS:279-287  w0 = [vec(shifted X); vec(shifted U)]
+    for (int k = 0; k <= N; ++k)
+      for (int i = 0; i < NX; ++i) { const int ks = (k + 1 <= N) ? k + 1 : N; g[q2++] = x[ks * NZ + i]; }
+    for (int k = 0; k < N; ++k)
+      for (int i = 0; i < NU; ++i) { const int ks = (k + 1 < N) ? k + 1 : N - 1; g[q2++] = x[ks * NZ + NX + i]; }
+  } else {
+    for (int i = 0; i < L.n; ++i) g[i] = x[i];
+  }
+}
+
+template <class Model>
+__global__ void lp_end_kernel(const LoopIO io, const LoopBufs lb, long B) {
+  constexpr int NX = Model::NX, NU = Model::NU;
+  const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int steps = lb.steps[b];
+  if (io.out_steps) io.out_steps[b] = steps;
+  if (io.out_iters) io.out_iters[b] = lb.iters_total[b];
+  if (io.out_status) io.out_status[b] = lb.worst[b];
+  double* os = io.out_states + b * (long)(io.n_steps + 1) * NX;
+  double* oc = io.out_controls + b * (long)io.n_steps * NU;
+  for (int t = steps; t < io.n_steps; ++t) {
+    for (int i = 0; i < NX; ++i) os[(t + 1) * NX + i] = lb.state[b * NX + i];
+    for (int i = 0; i < NU; ++i) oc[t * NU + i] = 0.0;
+  }
+}
 #endif  // __CUDACC__
 
 }  // namespace mpcv

@@ -19,6 +19,8 @@ struct mpcv_phase_state {
   int* retry = nullptr;
   int* slow = nullptr;
   double* slab2 = nullptr;          // second workspace slab (repack target)
+  LoopBufs lb = {};                 // closed-loop driver buffers
+  long lb_cap = 0;
   size_t slab2_doubles = 0;
   PhaseCtrl* ctrl = nullptr;
   SolveIO* d_io = nullptr;
@@ -31,6 +33,14 @@ struct mpcv_phase_state {
   long graph_stride = 0;
 };
 
+static void loop_free(mpcv_phase_state* s) {
+  void* ptrs[] = {s->lb.x0, s->lb.p, s->lb.x, s->lb.f, s->lb.state, s->lb.status, s->lb.iters, s->lb.active,
+                  s->lb.steps, s->lb.iters_total, s->lb.worst};
+  for (void* q : ptrs) if (q) cudaFree(q);
+  s->lb = LoopBufs{};
+  s->lb_cap = 0;
+}
+
 static void phase_free(mpcv_phase_state* s) {
   if (!s) return;
   if (s->exec) cudaGraphExecDestroy(s->exec);
@@ -40,6 +50,7 @@ static void phase_free(mpcv_phase_state* s) {
   if (s->retry) cudaFree(s->retry);
   if (s->slow) cudaFree(s->slow);
   if (s->slab2) cudaFree(s->slab2);
+  loop_free(s);
   if (s->ctrl) cudaFree(s->ctrl);
   if (s->d_io) cudaFree(s->d_io);
   if (s->h_ctrl) cudaFreeHost(s->h_ctrl);
@@ -272,6 +283,50 @@ static int launch_solve_phased(mpcv_handle* h, const SolveIO& io, long B, cudaSt
   return phase_host_loop<Model>(h, st);
 }
 
+// closed loop: per MPC step  prepare -> solve (graph) -> apply, all stream-ordered
+template <class Model>
+static int launch_loop_phased(mpcv_handle* h, const LoopIO& io, long B, cudaStream_t st) {
+  if (B <= 0) return 0;
+  if (int rc = phase_ensure(h, B)) return rc;
+  mpcv_phase_state* s = h->phase;
+  if (B > s->lb_cap) {
+    loop_free(s);
+    const size_t n = h->n_var, np = h->n_p, nx = h->nx;
+    CUDA_OK(cudaMalloc(&s->lb.x0, B * n * sizeof(double)));
+    CUDA_OK(cudaMalloc(&s->lb.p, B * np * sizeof(double)));
+    CUDA_OK(cudaMalloc(&s->lb.x, B * n * sizeof(double)));
+    CUDA_OK(cudaMalloc(&s->lb.f, B * sizeof(double)));
+    CUDA_OK(cudaMalloc(&s->lb.state, B * nx * sizeof(double)));
+    CUDA_OK(cudaMalloc(&s->lb.status, B * sizeof(int)));
+    CUDA_OK(cudaMalloc(&s->lb.iters, B * sizeof(int)));
+    CUDA_OK(cudaMalloc(&s->lb.active, B * sizeof(int)));
+    CUDA_OK(cudaMalloc(&s->lb.steps, B * sizeof(int)));
+    CUDA_OK(cudaMalloc(&s->lb.iters_total, B * sizeof(int)));
+    CUDA_OK(cudaMalloc(&s->lb.worst, B * sizeof(int)));
+    s->lb_cap = B;
+  }
+  const LoopBufs lb = s->lb;
+  const unsigned grid = (unsigned)((B + 127) / 128);
+  lp_begin_kernel<Model><<<grid, 128, 0, st>>>(h->L, io, lb, B);
+  h->launches++;
+  long long* const lat = h->latency_ns;
+  h->latency_ns = nullptr;
+  const SolveIO sio{lb.x0, io.lbx, io.ubx, lb.p, lb.x, lb.f, nullptr, nullptr, nullptr, lb.status, lb.iters, nullptr};
+  int rc = 0;
+  for (int t = 0; t < io.n_steps && rc == 0; ++t) {
+    lp_prepare_kernel<Model><<<grid, 128, 0, st>>>(h->L, io, lb, B, t);
+    rc = launch_solve_phased<Model>(h, sio, B, st);
+    lp_apply_kernel<Model><<<grid, 128, 0, st>>>(h->P, h->L, io, lb, B, t);
+    h->launches += 2;
+  }
+  h->latency_ns = lat;
+  if (rc) return rc;
+  lp_end_kernel<Model><<<grid, 128, 0, st>>>(io, lb, B);
+  h->launches++;
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 static int phase_sweeps(mpcv_handle* h, cudaStream_t st, int* sweeps, int* cumulative) {
   if (!h->phase || !h->phase->ctrl) { *sweeps = 0; *cumulative = 0; return 0; }
   CUDA_OK(cudaMemcpyAsync(h->phase->h_ctrl, h->phase->ctrl, sizeof(PhaseCtrl), cudaMemcpyDeviceToHost, st));
@@ -284,4 +339,4 @@ static int phase_sweeps(mpcv_handle* h, cudaStream_t st, int* sweeps, int* cumul
 #define MPCV_CAT2(a, b) a##b
 #define MPCV_CAT(a, b) MPCV_CAT2(a, b)
 extern const mpcv_phase_vtable MPCV_CAT(mpcv_phase_vtable_, MPCV_INST_MODEL) = {launch_solve_phased<ModelT>, phase_free,
-                                                                                phase_sweeps};
+                                                                                phase_sweeps, launch_loop_phased<ModelT>};

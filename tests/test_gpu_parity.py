@@ -304,7 +304,7 @@ def test_closed_loop_mpctools_unicycle_vs_3exemplo(mv):
     assert np.abs(r["controls"][0, :nst] - g[:nst, 3:5]).max() <= 1e-5
 
 
-@pytest.mark.parametrize("layout", [S.LAYOUT_THREAD, S.LAYOUT_WARP])
+@pytest.mark.parametrize("layout", [S.LAYOUT_THREAD, S.LAYOUT_WARP, S.LAYOUT_PHASED])
 def test_closed_loop_pendulum_vs_golden(mv, layout):
     g = common.golden("pendulum_invertpend.csv")
     sp0, lbx, ubx, pglob, _, _ = common.pendulum_setup(N=50, ntu=5)
@@ -318,8 +318,9 @@ def test_closed_loop_pendulum_vs_golden(mv, layout):
     assert np.abs(r["states"][0, :nst + 1, :4] - g[:nst + 1, :4]).max() <= 1e-4
 
 
-def test_closed_loop_batch_vs_oracle(mv):
-    solver = _solver(mv, problems.unicycle_multiple_shooting())
+@pytest.mark.parametrize("layout", [S.LAYOUT_THREAD, S.LAYOUT_PHASED])
+def test_closed_loop_batch_vs_oracle(mv, layout):
+    solver = _solver(mv, problems.unicycle_multiple_shooting(), layout=layout)
     lbx, ubx = problems.unicycle_bounds(solver.spec)
     x0s, _ = common.unicycle_batch(64, seed=9)
     tgt = np.tile([10, 10, 0.0], (64, 1))
