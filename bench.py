@@ -260,7 +260,8 @@ def main():
     lat_us = lat.cpu().numpy() / 1e3
     solver.disable_latency()
 
-    # ---- roofline of the dominant kernel (the solve kernel is the only kernel of a step) ----
+    # ---- roofline of the solve launch: ONE CUDA graph per step (init chain + a conditional WHILE node holding
+    # the 10-kernel iteration sweep); its duration is taken with CUDA events on the launching stream ----
     peak_tf, _ = mv.fp64_peak()
     kernel_ms = tk_ms / args.steps
     flops = iters_sum * FLOP_PER_ITER_C2
@@ -271,9 +272,15 @@ def main():
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    traffic = None      # DRAM bytes of one solve launch from the committed ncu launch list (profiles/)
+    try:
+        if B == B_PER_GPU and args.layout in (S.LAYOUT_AUTO, S.LAYOUT_PHASED):
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1b_traffic.json")))["dram_bytes_per_solve_launch"]
+    except Exception:
+        pass
     roofline = {
         "bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-        "traffic": None,
+        "traffic": traffic,
         "peak_source": "FP64 FMA peak measured in this run by mpcv_fp64_peak (MEASURED_PEAKS.json has no FP64 figure)",
         "flop_per_launch": flops, "kernel_ms": kernel_ms,
         "hbm": {"achieved_gbs": B * BYTES_PER_SOLVE_C2 / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
