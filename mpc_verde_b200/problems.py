@@ -129,3 +129,49 @@ def dynamic_bicycle_matrices(v, m=1200.0, a=1.5, b=2.0, Ca=55000.0, Jz=1350.0):
     Ac = np.array([[0, v, 1, 0], [0, 0, 0, 1], [0, 0, A33, A34], [0, 0, A43, A44]], dtype=float)
     Bc = np.array([[0.0], [0.0], [B31], [B41]])
     return Ac, Bc
+
+
+# ---- lateral-error bicycle (Trajectory Tracking/Phiref.py, Trjectory_tracking_le_LTV.py) ---------------
+LATERAL_AR, LATERAL_BR = -23.55, 61.99           # Phiref.py:47-48
+
+
+def lateral_error_matrices(uref, ar=LATERAL_AR, br=LATERAL_BR):
+    """Ac = [[0,u_ref,0],[0,0,1],[0,0,a_r]], Bc = [0,0,b_r]' (Phiref.py:87-90; LTV: u_ref = c[t], :158)."""
+    return np.array([[0.0, uref, 0.0], [0.0, 0.0, 1.0], [0.0, 0.0, ar]]), np.array([[0.0], [0.0], [br]])
+
+
+def lateral_error_par(a, b, Nt, Delta, ar=LATERAL_AR, br=LATERAL_BR):
+    """Reference builder of the lateral-error trackers, exactly as written (Phiref.py:124-155): per MPC step t
+    and horizon stage k the parameters (y_ref, phi_ref, r_ref, delta_ref) from finite differences of the path
+    (a, b).  Quirks kept: `par[1, k, t-1]` reads the previous step's slice — at t = 0 that is the still-zero
+    LAST slice — and `par[1, k-1, t-1]` wraps to the last stage at k = 0.  Returns par [4, Nt, Nsim]."""
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    Nsim = a.size
+    par = np.zeros((4, Nt, Nsim))
+    p = np.zeros((Nt, 4))
+    for t in range(Nsim):
+        for k in range(Nt):
+            if t + k > Nsim - 1:
+                p[k, 0] = b[Nsim - 1]
+                p[k, 1] = np.arctan2(b[Nsim - 1] - b[Nsim - 2], a[Nsim - 1] - a[Nsim - 2])
+            elif t + k == 0:
+                p[k, 0] = b[k + t]
+                p[k, 1] = 0.0
+            else:
+                p[k, 0] = b[k + t]
+                p[k, 1] = np.arctan2(b[k + t] - b[k + t - 1], a[k + t] - a[k + t - 1])
+            if t + k < 2:
+                plus = np.arctan2(b[k + 1 + t] - b[k + t], a[k + 1 + t] - a[k + t])
+                plus2 = np.arctan2(b[k + 2 + t] - b[k + 1 + t], a[k + 2 + t] - a[k + 1 + t])
+                p[k, 2] = (plus - p[k, 1]) / Delta
+                p[k, 3] = (((plus2 - 2 * plus + p[k, 1]) / Delta ** 2) - ar * p[k, 2]) / br
+            elif t + k > Nsim - 3:
+                p[k, 2] = (p[k, 1] - par[1, k, t - 1]) / Delta
+                p[k, 3] = (((p[k, 1] - 2 * par[1, k, t - 1] + par[1, k - 1, t - 1]) / Delta ** 2) - ar * p[k, 2]) / br
+            else:
+                plus = np.arctan2(b[k + 1 + t] - b[k + t], a[k + 1 + t] - a[k + t])
+                p[k, 2] = (plus - par[1, k, t - 1]) / (2 * Delta)
+                p[k, 3] = (((plus - 2 * p[k, 1] + par[1, k, t - 1]) / Delta ** 2) - ar * p[k, 2]) / br
+            par[:, k, t] = p[k, :]
+    return par

@@ -41,3 +41,28 @@ def pendulum_batch(sp, pglob, B, seed=20262):
     stage = np.tile([10.0, 0.0, 0.0, 0.0, 0.0], sp.N)
     p = np.concatenate([x0, np.tile(pglob, (B, 1)), np.tile(stage, (B, 1))], 1)
     return x0, p
+
+
+def lateral_error_closed_loop(solve_fn, ltv, nsim=None):
+    """The MPC loop of Trajectory Tracking/Phiref.py:156-200 (LTI; the commented block :157-171 is the LTV
+    variant that produced dados.csv): Nt=5, Ntu=1 (one free move, then blocked), Q=diag(10,1,0), R=0.01,
+    |delta| <= 0.3491, uprev = 0, solver rebuilt every step from the plant state, exact-ZOH plant.
+    solve_fn(spec, w0[B,n], lbx, ubx, p[B,n_p]) -> x[B,n].  Returns (u [Nsim], x [Nsim+1,3], par)."""
+    g = golden("lane_change.csv")
+    a, b, c = g[:, 0], g[:, 1], g[:, 2]
+    Nt, Delta = 5, 0.05
+    Nsim = a.size if nsim is None else nsim
+    sp = S.linear_tracking(3, Nt, Q=(10.0, 1.0, 0.0), R=0.01, T=Delta, R1=0.0, ntu=1)
+    lbx, ubx = problems.control_box(sp, -0.3491, 0.3491)
+    par = problems.lateral_error_par(a, b, Nt, Delta)
+    x = np.zeros((Nsim + 1, 3))
+    u = np.zeros(Nsim)
+    for t in range(Nsim):
+        Ac, Bc = problems.lateral_error_matrices(c[t] if ltv else c.mean())
+        A, Bd = problems.c2d(Ac, Bc, Delta)
+        xa = np.concatenate([x[t], [0.0]])                       # state augmented with uprev = 0
+        p = np.concatenate([xa, A.ravel(), Bd.ravel(), par[:, :, t].T.ravel()])[None, :]
+        sol = solve_fn(sp, problems.cold_start(sp, xa[None, :]), lbx, ubx, p)
+        u[t] = sol[0, sp.nx]
+        x[t + 1] = A @ x[t] + Bd[:, 0] * u[t]
+    return u, x, par

@@ -318,6 +318,31 @@ def test_closed_loop_pendulum_vs_golden(mv, layout):
     assert np.abs(r["states"][0, :nst + 1, :4] - g[:nst + 1, :4]).max() <= 1e-4
 
 
+def test_lateral_error_lti_and_ltv_closed_loops_vs_dados(mv):
+    """Trajectory Tracking/dados2.csv (LTI) and dados.csv (LTV): 500 MPC steps each, the solver called once per
+    step with the reference's own per-step parameters (Phiref.py:124-200), exact-ZOH plant (the reference's is
+    CVODES, ~1e-6)."""
+    cache = {}
+
+    def solve(sp, w0, lbx, ubx, p):
+        key = bytes(sp)
+        if key not in cache:
+            cache[key] = _solver(mv, {"spec": sp})
+        sol = cache[key](x0=w0, lbx=lbx, ubx=ubx, p=p, outputs=("x", "f"))
+        assert cache[key].stats()["success"]
+        return np.atleast_2d(sol["x"])
+
+    g2 = common.golden("lateral_lti_dados2.csv")
+    u, x, par = common.lateral_error_closed_loop(solve, ltv=False)
+    assert np.abs(par[:, 0, :].T - g2[:, 6:10]).max() <= 1e-12
+    assert np.abs(u - g2[:, 3]).max() <= 1e-5
+    assert np.abs(x[1:] - g2[:, 0:3]).max() <= 1e-4
+    g1 = common.golden("lateral_ltv_dados.csv")
+    u, x, _ = common.lateral_error_closed_loop(solve, ltv=True)
+    assert np.abs(u - g1[:, 3]).max() <= 1e-5
+    assert np.abs(x[1:] - g1[:, 0:3]).max() <= 1e-4
+
+
 @pytest.mark.parametrize("layout", [S.LAYOUT_THREAD, S.LAYOUT_PHASED])
 def test_closed_loop_batch_vs_oracle(mv, layout):
     solver = _solver(mv, problems.unicycle_multiple_shooting(), layout=layout)

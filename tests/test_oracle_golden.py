@@ -102,3 +102,19 @@ def test_pendulum_c2d_and_closed_loop_vs_golden():
     assert abs(r["controls"][0, 0, 0] - (-60.84425718936204)) <= 1e-6
     assert np.abs(r["controls"][0, :nst, 0] - g[:nst, 4]).max() <= 1e-5
     assert np.abs(r["states"][0, :, :4] - g[:, :4]).max() <= 1e-4
+
+
+def test_lateral_error_lti_and_ltv_closed_loops_vs_dados():
+    """Trajectory Tracking/dados2.csv (LTI, Phiref.py:379-381) and dados.csv (LTV variant): the reference's
+    own parameter builder (columns yref..deltaref) and the 500-step closed loops.  The reference plant is
+    CVODES (integrator tolerance ~1e-6), here exact ZOH."""
+    solve = lambda sp, w0, lbx, ubx, p: O.solve(sp, w0, lbx, ubx, p)["x"]
+    g2 = common.golden("lateral_lti_dados2.csv")
+    u, x, par = common.lateral_error_closed_loop(solve, ltv=False)
+    assert np.abs(par[:, 0, :].T - g2[:, 6:10]).max() <= 1e-12          # the `par` builder, bit-level
+    assert np.abs(u - g2[:, 3]).max() <= 1e-5
+    assert np.abs(x[1:] - g2[:, 0:3]).max() <= 1e-4
+    g1 = common.golden("lateral_ltv_dados.csv")
+    u, x, _ = common.lateral_error_closed_loop(solve, ltv=True)
+    assert np.abs(u - g1[:, 3]).max() <= 1e-5
+    assert np.abs(x[1:] - g1[:, 0:3]).max() <= 1e-4
