@@ -23,6 +23,7 @@ static const mpcv_model_vtable* vtable_of(int model) {
     case 4: return &mpcv_model_vtable_4;
     case 5: return &mpcv_model_vtable_5;
     case 6: return &mpcv_model_vtable_6;
+    case 7: return &mpcv_model_vtable_7;
     default: return nullptr;
   }
 }
@@ -36,6 +37,7 @@ const mpcv_phase_vtable* mpcv_phase_vtable_of(int model) {
     case 4: return &mpcv_phase_vtable_4;
     case 5: return &mpcv_phase_vtable_5;
     case 6: return &mpcv_phase_vtable_6;
+    case 7: return &mpcv_phase_vtable_7;
     default: return nullptr;
   }
 }

@@ -65,4 +65,4 @@ const mpcv_phase_vtable* mpcv_phase_vtable_of(int model);
   extern const mpcv_model_vtable mpcv_model_vtable_##id; \
   extern const mpcv_phase_vtable mpcv_phase_vtable_##id;
 MPCV_DECLARE_MODEL(0) MPCV_DECLARE_MODEL(1) MPCV_DECLARE_MODEL(2) MPCV_DECLARE_MODEL(3)
-MPCV_DECLARE_MODEL(4) MPCV_DECLARE_MODEL(5) MPCV_DECLARE_MODEL(6)
+MPCV_DECLARE_MODEL(4) MPCV_DECLARE_MODEL(5) MPCV_DECLARE_MODEL(6) MPCV_DECLARE_MODEL(7)

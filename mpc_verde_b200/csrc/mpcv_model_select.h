@@ -14,6 +14,8 @@ using ModelT = mpcv::Linear<4, false>;
 using ModelT = mpcv::Linear<4, true>;
 #elif MPCV_INST_MODEL == 6
 using ModelT = mpcv::Linear<3, true>;
+#elif MPCV_INST_MODEL == 7
+using ModelT = mpcv::FrenetBicycle;
 #else
 #error "unknown MPCV_INST_MODEL"
 #endif

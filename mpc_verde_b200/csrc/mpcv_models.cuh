@@ -374,4 +374,209 @@ struct Linear {
   }
 };
 
+// ---------------------------------------------------------------------------------------
+// Frenet kinematic bicycle — Trajectory Tracking/test2.py
+//   ode  (:103-112)  ydot = v sin(phi-phit),
+//                    phidot = v (tan(delta/L) - kappat/(1-(y-yt) kappat) cos(phi-phit)),  vdot = a
+//   cost (:42-51)    (l1 (v-vdes)^2 + l2 (y-yt)^2 + l3 (phi-phit)^2 + l4 a^2 + l5 (tan delta - L kappat)^2)/(Nt+1)
+//   RK4, M sub-steps (:118); bounds |delta| <= 0.384, |a| <= 2, |d delta| <= 0.1225 (:31-36,55-59)
+// State (y, phi, v, delta_prev), control (d_delta, a) with delta = delta_prev + d_delta: MPCTools' Du bound
+// becomes a box on the control and the delta bound a box on the next state.  Stage parameters exactly as the
+// code unpacks them: [yt, phit, kappat] = p[:3], vdes = p[3] (the script's builder fills p[2]/p[3] swapped,
+// :89-99 — follow the code).  Weights: Q = (l2, l3, l1, l5), R[1] = l4; extra = (L, Nt+1).
+//
+// Derivatives: the RK4 map depends on z5 = (y, phi, v, delta, a) only.  A second-order forward-mode jet
+// (value, gradient, packed Hessian over z5) is pushed through the four stages; the node cost is
+// differentiated by hand; the chain rule delta = delta_prev + d_delta duplicates the delta row / column.
+// ---------------------------------------------------------------------------------------
+struct Jet5 {
+  double v, g[5], h[15];
+};
+MPCV_HD Jet5 jet_const(double c) {
+  Jet5 r; r.v = c;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) r.g[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 15; ++i) r.h[i] = 0.0;
+  return r;
+}
+MPCV_HD Jet5 jet_var(double c, int k) { Jet5 r = jet_const(c); r.g[k] = 1.0; return r; }
+MPCV_HD Jet5 jet_add(const Jet5& a, const Jet5& b) {
+  Jet5 r; r.v = a.v + b.v;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) r.g[i] = a.g[i] + b.g[i];
+#pragma unroll
+  for (int i = 0; i < 15; ++i) r.h[i] = a.h[i] + b.h[i];
+  return r;
+}
+MPCV_HD Jet5 jet_axpy(double s, const Jet5& a, const Jet5& b) {   // s*a + b
+  Jet5 r; r.v = s * a.v + b.v;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) r.g[i] = s * a.g[i] + b.g[i];
+#pragma unroll
+  for (int i = 0; i < 15; ++i) r.h[i] = s * a.h[i] + b.h[i];
+  return r;
+}
+MPCV_HD Jet5 jet_scale(double s, const Jet5& a) {
+  Jet5 r; r.v = s * a.v;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) r.g[i] = s * a.g[i];
+#pragma unroll
+  for (int i = 0; i < 15; ++i) r.h[i] = s * a.h[i];
+  return r;
+}
+MPCV_HD Jet5 jet_mul(const Jet5& a, const Jet5& b) {
+  Jet5 r; r.v = a.v * b.v;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) r.g[i] = a.v * b.g[i] + b.v * a.g[i];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+#pragma unroll
+    for (int j = 0; j <= i; ++j)
+      r.h[tri(i, j)] = a.v * b.h[tri(i, j)] + b.v * a.h[tri(i, j)] + a.g[i] * b.g[j] + a.g[j] * b.g[i];
+  }
+  return r;
+}
+// r = f(a) given f, f', f'' at a.v
+MPCV_HD Jet5 jet_fun(const Jet5& a, double f, double f1, double f2) {
+  Jet5 r; r.v = f;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) r.g[i] = f1 * a.g[i];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+#pragma unroll
+    for (int j = 0; j <= i; ++j) r.h[tri(i, j)] = f1 * a.h[tri(i, j)] + f2 * a.g[i] * a.g[j];
+  }
+  return r;
+}
+
+struct FrenetBicycle {
+  static constexpr int NX = 4, NU = 2, NZ = 6;
+  static constexpr int NPG = 0, NPS = 4;
+  static constexpr bool HAS_UPREV = true;
+  static constexpr int MODEL_ID = MPCV_MODEL_FRENET_BICYCLE;
+
+  template <class PS>
+  MPCV_HD static void rhs(double L, const double* X, double tdl, double a, PS ps, double* dx) {
+    double s, c;
+    sincos_(X[1] - ps[1], &s, &c);
+    dx[0] = X[2] * s;
+    dx[1] = X[2] * (tdl - (ps[2] / (1.0 - (X[0] - ps[0]) * ps[2])) * c);
+    dx[2] = a;
+  }
+
+  template <class PS>
+  MPCV_HD static double node_cost(const Params& P, const double* x, double delta, double a, PS ps) {
+    const double ev = x[2] - ps[3], ey = x[0] - ps[0], ep = x[1] - ps[1];
+    const double z = tan(delta) - P.extra[0] * ps[2];
+    return (ev * ev * P.Q[2] + ey * ey * P.Q[0] + ep * ep * P.Q[1] + a * a * P.R[1] + z * z * P.Q[3]) / P.extra[1];
+  }
+
+  template <class PG, class PS>
+  MPCV_HD static void val(const Params& P, const double* x, const double* u, PG, PS ps, double* xn, double* q) {
+    const int M = P.M;
+    const double DT = P.T / M, L = P.extra[0];
+    const double delta = x[3] + u[0], a = u[1], tdl = tan(delta / L);
+    double X[3] = {x[0], x[1], x[2]};
+    for (int j = 0; j < M; ++j) {
+      double k1[3], k2[3], k3[3], k4[3], t[3];
+      rhs(L, X, tdl, a, ps, k1);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) t[i] = X[i] + DT / 2 * k1[i];
+      rhs(L, t, tdl, a, ps, k2);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) t[i] = X[i] + DT / 2 * k2[i];
+      rhs(L, t, tdl, a, ps, k3);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) t[i] = X[i] + DT * k3[i];
+      rhs(L, t, tdl, a, ps, k4);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) X[i] = X[i] + DT / 6 * (k1[i] + 2 * k2[i] + 2 * k3[i] + k4[i]);
+    }
+    xn[0] = X[0]; xn[1] = X[1]; xn[2] = X[2]; xn[3] = delta;
+    *q = node_cost(P, x, delta, a, ps);
+  }
+
+  // jet of the right-hand side: X = (y, phi, v) jets, tdl = jet of tan(delta/L), aj = jet of a
+  template <class PS>
+  MPCV_HD static void rhs_jet(const Jet5* X, const Jet5& tdl, const Jet5& aj, PS ps, Jet5* dx) {
+    double s, c;
+    sincos_(X[1].v - ps[1], &s, &c);
+    const Jet5 sj = jet_fun(X[1], s, c, -s), cj = jet_fun(X[1], c, -s, -c);
+    dx[0] = jet_mul(X[2], sj);
+    // w = kappat / (1 - (y - yt) kappat) as a function of y:  w' = kappat^2 / den^2,  w'' = 2 kappat^3 / den^3
+    const double kap = ps[2], den = 1.0 - (X[0].v - ps[0]) * kap, w = kap / den;
+    const Jet5 wj = jet_fun(X[0], w, w * w, 2.0 * w * w * w);
+    const Jet5 inner = jet_axpy(-1.0, jet_mul(wj, cj), tdl);
+    dx[1] = jet_mul(X[2], inner);
+    dx[2] = aj;
+  }
+
+  template <class PG, class PS>
+  MPCV_HD static void der(const Params& P, const double* x, const double* u, PG, PS ps, const double* lam,
+                          double df, bool want_hess, double* xn, double* A, double* B, double* q, double* g,
+                          double* W) {
+    const int M = P.M;
+    const double DT = P.T / M, L = P.extra[0];
+    const double delta = x[3] + u[0], a = u[1];
+    // independent quantities z5 = (y, phi, v, delta, a)
+    Jet5 X[3] = {jet_var(x[0], 0), jet_var(x[1], 1), jet_var(x[2], 2)};
+    const Jet5 dj = jet_var(delta, 3), aj = jet_var(a, 4);
+    const double t = tan(delta / L), sec2 = 1.0 + t * t;
+    const Jet5 tdl = jet_fun(dj, t, sec2 / L, 2.0 * t * sec2 / (L * L));
+    for (int j = 0; j < M; ++j) {
+      Jet5 k1[3], k2[3], k3[3], k4[3], tmp[3];
+      rhs_jet(X, tdl, aj, ps, k1);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) tmp[i] = jet_axpy(DT / 2, k1[i], X[i]);
+      rhs_jet(tmp, tdl, aj, ps, k2);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) tmp[i] = jet_axpy(DT / 2, k2[i], X[i]);
+      rhs_jet(tmp, tdl, aj, ps, k3);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) tmp[i] = jet_axpy(DT, k3[i], X[i]);
+      rhs_jet(tmp, tdl, aj, ps, k4);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        const Jet5 s1 = jet_add(k1[i], k4[i]), s2 = jet_add(k2[i], k3[i]);
+        X[i] = jet_axpy(DT / 6, jet_axpy(2.0, s2, s1), X[i]);
+      }
+    }
+    xn[0] = X[0].v; xn[1] = X[1].v; xn[2] = X[2].v; xn[3] = delta;
+    // z6 = (y, phi, v, delta_prev, d_delta, a) -> z5 index
+    const int m[6] = {0, 1, 2, 3, 3, 4};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) A[i * 4 + j] = X[i].g[m[j]];
+      B[i * 2 + 0] = X[i].g[3];
+      B[i * 2 + 1] = X[i].g[4];
+    }
+    A[12] = 0; A[13] = 0; A[14] = 0; A[15] = 1;
+    B[6] = 1; B[7] = 0;
+    // node cost, by hand
+    const double div = P.extra[1];
+    const double ev = x[2] - ps[3], ey = x[0] - ps[0], ep = x[1] - ps[1];
+    const double td = tan(delta), sd2 = 1.0 + td * td, z = td - L * ps[2];
+    *q = (ev * ev * P.Q[2] + ey * ey * P.Q[0] + ep * ep * P.Q[1] + a * a * P.R[1] + z * z * P.Q[3]) / div;
+    const double gd = 2.0 * P.Q[3] * z * sd2 / div;
+    g[0] = 2.0 * P.Q[0] * ey / div; g[1] = 2.0 * P.Q[1] * ep / div; g[2] = 2.0 * P.Q[2] * ev / div;
+    g[3] = gd; g[4] = gd; g[5] = 2.0 * P.R[1] * a / div;
+    if (want_hess) {
+      const double hdd = 2.0 * P.Q[3] * (sd2 * sd2 + z * 2.0 * sd2 * td) / div;
+      const double hq5[5] = {2.0 * P.Q[0] / div, 2.0 * P.Q[1] / div, 2.0 * P.Q[2] / div, hdd, 2.0 * P.R[1] / div};
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+          const int a5 = m[i] >= m[j] ? m[i] : m[j], b5 = m[i] >= m[j] ? m[j] : m[i];
+          double v = lam[0] * X[0].h[tri(a5, b5)] + lam[1] * X[1].h[tri(a5, b5)] + lam[2] * X[2].h[tri(a5, b5)];
+          if (a5 == b5) v += df * hq5[a5];
+          W[tri(i, j)] = v;
+        }
+      }
+    }
+  }
+};
+
 }  // namespace mpcv

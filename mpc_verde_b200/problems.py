@@ -45,6 +45,24 @@ def unicycle_tracking(N=10, T=0.2, M=1, Q=(1.0, 1.0, 0.1), R=S.UNICYCLE_R):
                  "[x0-X0 ; RK4(X_k,U_k)-X_{k+1}]", "[x0(3); p_0(5) ... p_{N-1}(5)]")
 
 
+def frenet_bicycle(N=20, T=0.05, M=1, L=3.5, lam=(2.5, 1.75, 2.5, 0.4, 10.0)):
+    """Trajectory Tracking/test2.py:20-122 (Frenet kinematic bicycle, RK4 M=1, per-stage p = (yt, phit, kappat, vdes))."""
+    return _prob(S.frenet_bicycle(N, T, M, L, lam),
+                 "sum_k (l1 (v-vdes)^2 + l2 (y-yt)^2 + l3 (phi-phit)^2 + l4 a^2 + l5 (tan delta - L kappat)^2)/(Nt+1)",
+                 "[X0,U0,...,X_N], X = (y, phi, v, delta_prev), U = (d_delta, a)", "[xbar - X0 ; F(X_k,U_k) - X_{k+1}]",
+                 "[xbar ; p_0 .. p_{N-1}]")
+
+
+def frenet_bounds(spec, delta_max=0.384, a_max=2.0, ddelta_max=0.1225):
+    """test2.py:31-36,55-59: |delta| <= 0.384 (box on the delta_prev state of stages 1..N), |a| <= 2,
+    |d delta| <= 0.1225 (MPCTools' Du bound = box on the control)."""
+    lbx, ubx = control_box(spec, (-ddelta_max, -a_max), (ddelta_max, a_max),
+                           (-np.inf, -np.inf, -np.inf, -delta_max), (np.inf, np.inf, np.inf, delta_max))
+    nz = spec.nx + spec.nu
+    lbx[3], ubx[3] = -np.inf, np.inf          # stage 0: delta_prev is data (pinned by the x0 equality)
+    return lbx, ubx
+
+
 def linear_tracking(nx, N, Q, R, T=0.0, R1=None, ntu=0):
     """MPCTools linear trackers (lateral-error bicycle nx=3, dynamic bicycle / cart-pendulum nx=4)."""
     sp = S.linear_tracking(nx, N, Q, R, T, R1, ntu)

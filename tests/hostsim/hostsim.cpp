@@ -121,6 +121,7 @@ static int hs_der_t(const mpcv_spec* s, const double* z, const double* pstage, c
     case MPCV_MODEL_LINEAR4: return CALL(Linear<4 HS_COMMA false>);                            \
     case MPCV_MODEL_LINEAR4_DU: return CALL(Linear<4 HS_COMMA true>);                          \
     case MPCV_MODEL_LINEAR3_DU: return CALL(Linear<3 HS_COMMA true>);                          \
+    case MPCV_MODEL_FRENET_BICYCLE: return CALL(FrenetBicycle);                               \
     default: return -22;                                                                       \
   }
 #define HS_COMMA ,

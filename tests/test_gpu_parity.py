@@ -76,6 +76,8 @@ def test_rollout_matches_oracle_random(mv):
     lambda: problems.linear_tracking(4, 5, (1, 2, 3, 4), 1.0),
     lambda: problems.linear_tracking(4, 5, (1.44, 0, 1, 0), 0.0, R1=1e-4),
     lambda: problems.linear_tracking(3, 5, (10, 1, 0, 0), 0.01, R1=0.5),
+    lambda: problems.frenet_bicycle(N=20, T=0.05, M=1),
+    lambda: problems.frenet_bicycle(N=5, T=0.1, M=2),
 ])
 def test_stage_derivatives_vs_oracle_ad(mv, mk):
     solver = _solver(mv, mk())
@@ -84,6 +86,9 @@ def test_stage_derivatives_vs_oracle_ad(mv, mk):
     B = 256
     z = rng.normal(size=(B, sp.nx + sp.nu)) * 2
     ps = rng.normal(size=(B, max(sp.npg + sp.nps, 1)))
+    if sp.model == S.MODEL_FRENET_BICYCLE:
+        z *= 0.15                     # stay away from the poles of tan(delta) and of 1/(1-(y-yt) kappat)
+        ps *= 0.1
     lam = rng.normal(size=(B, sp.nx)) * 3
     a = O.stage_derivs(sp, z, ps, lam)
     b = solver.stage_derivs(z, ps, lam)
@@ -236,7 +241,19 @@ def test_unicycle_tracking_batch_vs_oracle(mv):
     _compare_solve(solver, sp, problems.cold_start(sp, x0), lbx, ubx, p, True)
 
 
-@pytest.mark.parametrize("layout", [S.LAYOUT_THREAD, S.LAYOUT_WARP])
+@pytest.mark.parametrize("layout", [S.LAYOUT_PHASED, S.LAYOUT_THREAD])
+def test_frenet_bicycle_batch_vs_oracle(mv, layout):
+    """Trajectory Tracking/test2.py: nonlinear Frenet bicycle, N=20, steering-rate box on the control and
+    steering box on the delta_prev state."""
+    from tests.test_hostsim import frenet_batch
+    solver = _solver(mv, problems.frenet_bicycle(N=20, T=0.05, M=1), layout=layout)
+    sp = solver.spec
+    lbx, ubx = problems.frenet_bounds(sp)
+    x0, p = frenet_batch(sp, 512)
+    _compare_solve(solver, sp, problems.cold_start(sp, x0), lbx, ubx, p, True)
+
+
+@pytest.mark.parametrize("layout", [S.LAYOUT_THREAD, S.LAYOUT_WARP, S.LAYOUT_PHASED])
 def test_pendulum_batch_vs_oracle(mv, layout):
     sp0, lbx, ubx, pglob, _, _ = common.pendulum_setup(N=40, ntu=0, discretisation="rk4")
     solver = _solver(mv, {"spec": sp0}, layout=layout)
@@ -245,7 +262,7 @@ def test_pendulum_batch_vs_oracle(mv, layout):
     _compare_solve(solver, sp, problems.cold_start(sp, x0), lbx, ubx, p, True)
 
 
-@pytest.mark.parametrize("layout", [S.LAYOUT_THREAD, S.LAYOUT_WARP])
+@pytest.mark.parametrize("layout", [S.LAYOUT_THREAD, S.LAYOUT_WARP, S.LAYOUT_PHASED])
 def test_dynamic_bicycle_n50_vs_oracle(mv, layout):
     N, dt, B = 50, 0.05, 128
     rng = np.random.default_rng(7)

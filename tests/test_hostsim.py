@@ -21,6 +21,8 @@ MODELS = [
     ("lin4", lambda: S.linear_tracking(4, 5, (1, 2, 3, 4), 1.0)),
     ("lin4du", lambda: S.linear_tracking(4, 5, (1.44, 0, 1, 0), 0.0, R1=1e-4)),
     ("lin3du", lambda: S.linear_tracking(3, 5, (10, 1, 0, 0), 0.01, R1=0.5)),
+    ("frenet", lambda: S.frenet_bicycle(N=20, T=0.05, M=1)),
+    ("frenet_m2", lambda: S.frenet_bicycle(N=5, T=0.1, M=2)),
 ]
 
 
@@ -31,6 +33,9 @@ def test_hand_derivatives_vs_ad(name, mk):
     B = 64
     z = rng.normal(size=(B, sp.nx + sp.nu)) * 2
     ps = rng.normal(size=(B, max(sp.npg + sp.nps, 1)))
+    if name.startswith("frenet"):
+        z *= 0.15                     # stay away from the poles of tan(delta) and of 1/(1-(y-yt) kappat)
+        ps *= 0.1
     lam = rng.normal(size=(B, sp.nx)) * 3
     a, b = O.stage_derivs(sp, z, ps, lam), H.stage_derivs(sp, z, ps, lam)
     for k in a:
@@ -130,3 +135,32 @@ def test_phase_pipeline_schedule_is_bit_identical_to_one_kernel_solve():
     lbt, ubt = problems.control_box(spt, (-1, -math.pi / 4), (1, math.pi / 4), (-20, -2, -np.inf), (20, 2, np.inf))
     wt = problems.cold_start(spt, x0)
     assert _same(H.solve(spt, wt, lbt, ubt, pt), H.solve(spt, wt, lbt, ubt, pt, phased=True))
+
+
+def frenet_batch(sp, B, seed=20265):
+    """Synthetic C4-secondary batch: lane-change-like references (Trajectory Tracking/test2.py:79-100 unpacks
+    p = (yt, phit, kappat, vdes)), random lateral / heading / speed offsets."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(sp.N) * sp.T
+    amp = rng.uniform(0.5, 1.5, (B, 1))
+    yt = amp * 0.5 * (1 - np.cos(0.8 * t))[None, :]
+    phit = amp * 0.4 * np.sin(0.8 * t)[None, :] * 0.2
+    kap = amp * 0.02 * np.cos(0.8 * t)[None, :]
+    vdes = np.tile(rng.uniform(0.4, 0.8, (B, 1)), (1, sp.N))
+    stage = np.stack([yt, phit, kap, vdes], 2).reshape(B, -1)
+    x0 = np.stack([rng.normal(size=B) * 0.1, rng.normal(size=B) * 0.05, vdes[:, 0] + rng.normal(size=B) * 0.05,
+                   np.zeros(B)], 1)
+    return x0, np.concatenate([x0, stage], 1)
+
+
+def test_frenet_bicycle_ipm_vs_oracle():
+    sp = S.frenet_bicycle(N=20, T=0.05, M=1)
+    lbx, ubx = problems.frenet_bounds(sp)
+    x0, p = frenet_batch(sp, 48)
+    w0 = problems.cold_start(sp, x0)
+    a, b, c = O.solve(sp, w0, lbx, ubx, p), H.solve(sp, w0, lbx, ubx, p), H.solve(sp, w0, lbx, ubx, p, phased=True)
+    assert np.all(a["status"] == 0) and np.all(b["status"] == 0)
+    assert np.mean(a["iters"] == b["iters"]) >= 0.95
+    assert np.abs(a["x"] - b["x"]).max() <= 1e-8
+    assert np.abs(a["f"] - b["f"]).max() <= 1e-9 * (1 + np.abs(a["f"]).max())
+    assert _same(b, c)
