@@ -57,6 +57,7 @@ struct PhaseCtrl {
   int pad;
 };
 constexpr int kRepackMin = 512;     // do not bother to repack fewer survivors than this
+constexpr int kTailBelow = 1024;    // at most this many active problems: leave the sweeps, finish in ph_tail_kernel
 constexpr int kWideBelow = 4096;    // below this many active problems the lane-group kernels use 32 lanes
 
 template <class Model, class WS, int LANES = 1>
@@ -181,6 +182,26 @@ struct Phase {
     const int st = ipm.line_search(true);
     if (st != 0) { finish(ipm, st, io, b, now); return; }
     ipm.save_state(kRunning);
+  }
+
+  // Straggler tail: run the remaining iterations of ONE problem to completion, all phases in sequence on
+  // the group's lanes (what Ipm::solve() does after its start-up), from the state the sweeps left behind.
+  // Precondition: a derivative sweep at the current iterate has been done (as at the top of every sweep).
+  MPCV_HD static void tail_body(const Params& P, const Layout& L, WS ws, const SolveIO& io, long b,
+                                const BndEntry* tab, Grp<LANES> g, long long now) {
+    IpmT ipm(P, L, ws, g, io.lbx, io.ubx, tab);
+    int st = ipm.load_state();
+    if (st != kRunning) return;
+    ipm.f_curr = ipm.sum_stage_costs();
+    for (;;) {
+      st = ipm.check_convergence_update_mu();
+      if (st != kRunning) break;
+      st = ipm.compute_direction();
+      if (st == 0) st = ipm.line_search(false);
+      if (st != 0) break;
+      ipm.eval_derivatives(true);
+    }
+    finish(ipm, st, io, b, now);
   }
 
   template <class I>
@@ -538,6 +559,26 @@ __global__ void __launch_bounds__(kPhaseThreads) ph_der_kernel(const __grid_cons
   }
 }
 
+// After the WHILE loop: the stragglers (at most kTailBelow problems, typically the 1-2 % that need 2-4x the
+// mean iteration count) finish here, one warp per problem, every phase in-kernel.  A sweep over so few
+// problems is pure launch-plus-latency floor (~200 us for 10 dependent launches); in here an iteration costs
+// what its own dependent chain costs and problems do not wait for each other.
+template <class Model>
+__global__ void __launch_bounds__(kWarpPhaseThreads) ph_tail_kernel(const __grid_constant__ PhaseArgs a) {
+  double* const slab = a.slab[a.ctrl->cur];
+  const int in = a.ctrl->sweep & 1;
+  const int n = a.ctrl->n_act[in];
+  const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((long)blockIdx.x * wpb >= n) return;
+  const SolveIO io = *a.io;
+  const BndEntry* tab = ph_bounds_table<Model>(a.P, a.L, io);
+  for (long e = (long)blockIdx.x * wpb + warp; e < n; e += (long)gridDim.x * wpb) {
+    const int b = a.act[in][e];
+    Phase<Model, WsStrided, 32>::tail_body(a.P, a.L, WsStrided::of(slab, a.L.total, b), io, b, tab, Grp<32>(lane),
+                                           io.ns ? ph_globaltimer() : 0);
+  }
+}
+
 // end of an iteration sweep: swap the lists and tell the WHILE node whether anyone is left
 static __global__ void ph_flip_kernel(PhaseCtrl* ctrl, cudaGraphConditionalHandle handle, int use_handle) {
   const int in = ctrl->sweep & 1, out = in ^ 1;
@@ -552,7 +593,7 @@ static __global__ void ph_flip_kernel(PhaseCtrl* ctrl, cudaGraphConditionalHandl
   ctrl->sweep += 1;
   ctrl->sweeps_total += 1;
   ctrl->sweeps_cum += 1;
-  if (use_handle) cudaGraphSetConditional(handle, ctrl->n_act[out] > 0 ? 1u : 0u);
+  if (use_handle) cudaGraphSetConditional(handle, ctrl->n_act[out] > kTailBelow ? 1u : 0u);
 }
 
 static __global__ void ph_begin_kernel(PhaseCtrl* ctrl, SolveIO* dst, const SolveIO io, int B) {

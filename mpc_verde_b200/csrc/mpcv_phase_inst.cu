@@ -199,6 +199,9 @@ static int phase_build_graph(mpcv_handle* h) {
   if (int rc = add_kernel(body, &b_slow, &b_accept, (void*)ph_slow_kernel<Model>, gr.warp, kWarpPhaseThreads, smem, a_init)) return rc;
   if (int rc = add_kernel(body, &b_der, &b_slow, (void*)ph_der_kernel<Model>, gr.stage, kPhaseThreads, smem, a_init)) return rc;
   if (int rc = add_kernel(body, &b_flip, &b_der, (void*)ph_flip_kernel, 1, 1, 0, a_flip)) return rc;
+  // the stragglers finish in one persistent kernel after the loop
+  cudaGraphNode_t n_tail;
+  if (int rc = add_kernel(g, &n_tail, &n_while, (void*)ph_tail_kernel<Model>, gr.warp, kWarpPhaseThreads, smem, a_init)) return rc;
   cudaGraphExec_t exec = nullptr;
   CUDA_OK(cudaGraphInstantiate(&exec, g, 0));
   s->graph = g;
@@ -239,8 +242,10 @@ static int phase_host_loop(mpcv_handle* h, cudaStream_t st) {
     }
     CUDA_OK(cudaMemcpyAsync(s->h_ctrl, s->ctrl, sizeof(PhaseCtrl), cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
-    if (s->h_ctrl->n_act[s->h_ctrl->sweep & 1] == 0) break;
+    if (s->h_ctrl->n_act[s->h_ctrl->sweep & 1] <= kTailBelow) break;
   }
+  ph_tail_kernel<Model><<<gr.warp, kWarpPhaseThreads, smem, st>>>(a);
+  h->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -259,6 +264,7 @@ static int launch_solve_phased(mpcv_handle* h, const SolveIO& io, long B, cudaSt
         phase_set_smem(ph_factor_kernel<Model>, smem) || phase_set_smem(ph_post_kernel<Model>, smem) ||
         phase_set_smem(ph_trial_kernel<Model>, smem) || phase_set_smem(ph_accept_kernel<Model>, smem) ||
         phase_set_smem(ph_retry_kernel<Model>, smem) || phase_set_smem(ph_slow_kernel<Model>, smem) ||
+        phase_set_smem(ph_tail_kernel<Model>, smem) ||
         phase_set_smem(ph_der_kernel<Model>, smem))
       return -EIO;
   }
@@ -276,7 +282,7 @@ static int launch_solve_phased(mpcv_handle* h, const SolveIO& io, long B, cudaSt
   }
   if (want_graph && s->exec) {
     CUDA_OK(cudaGraphLaunch(s->exec, st));
-    h->launches += 4;    // init chain; the sweeps are counted from the device (mpcv_phase_sweeps)
+    h->launches += 5;    // init chain + tail; the sweeps are counted from the device (mpcv_phase_sweeps)
     h->phase_graph_launches++;
     return 0;
   }

@@ -47,6 +47,8 @@ static int hs_solve_phased_t(const mpcv_spec* s, const SolveIO& io, long B, int*
   for (int k = 0; k < L.N; ++k) for (long b = 0; b < B; ++b) Ph::der_body(P, L, ws(b), io, k, true, tab.data());
   std::vector<int> retry, slow;
   const Grp<1> g1(0);
+  // (the GPU leaves the sweeps at <= kTailBelow problems and finishes them in ph_tail_kernel; the replay keeps
+  // sweeping — same phase functions, same results per problem)
   while (n_act[sweep & 1] > 0) {
     const int in = sweep & 1, out = in ^ 1;
     retry.clear(); slow.clear();

@@ -170,7 +170,7 @@ def test_phased_layout_equals_thread_layout(mv, hostloop, monkeypatch):
         out.append((sol, st["iter_count"]))
         if layout == S.LAYOUT_PHASED:
             sweeps = solver.phase_sweeps()
-            assert sweeps >= st["iter_count"].max() + 1 and (hostloop or sweeps == st["iter_count"].max() + 1)
+            assert 1 <= sweeps <= st["iter_count"].max() + 4      # the last <= 1024 problems finish in ph_tail_kernel
             # a second call on the same handle (graph re-launch) and a smaller batch (same graph, early exits)
             sol2 = solver(x0=problems.cold_start(sp, x0s), lbx=lbx, ubx=ubx, p=p)
             assert np.array_equal(sol2["x"], sol["x"]) and np.array_equal(sol2["f"], sol["f"])
