@@ -57,7 +57,10 @@ struct PhaseCtrl {
   int pad;
 };
 constexpr int kRepackMin = 512;     // do not bother to repack fewer survivors than this
-constexpr int kTailBelow = 1024;    // at most this many active problems: leave the sweeps, finish in ph_tail_kernel
+#ifndef MPCV_TAIL_BELOW
+#define MPCV_TAIL_BELOW 4096   /* measured: 512: 24.6 ms, 1024: 24.1, 2048: 23.7, 4096: 23.1, 8192: 23.6, 16384: 24.4, all: 77 */
+#endif
+constexpr int kTailBelow = MPCV_TAIL_BELOW;    // at most this many active problems: leave the sweeps, finish in ph_tail_kernel
 constexpr int kWideBelow = 4096;    // below this many active problems the lane-group kernels use 32 lanes
 
 template <class Model, class WS, int LANES = 1>

@@ -38,3 +38,25 @@ def reduce_stats(status, iters, group=None):
         dist.all_reduce(v, op=dist.ReduceOp.SUM, group=group)
         dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
     return {"problems": int(v[0]), "succeeded": int(v[1]), "iters_sum": int(v[2]), "iters_max": int(mx[0])}
+
+
+def gather_rows_equal(t, group=None):
+    """All-gather when every rank owns the same number of rows (weak scaling): one collective, no host
+    synchronisation, so it can run on a side stream underneath the next solve."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return t
+    world = dist.get_world_size(group)
+    out = torch.empty((world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+    return out
+
+
+def reduce_stats_device(status, iters, group=None):
+    """reduce_stats without host round trips: returns device tensors [problems, succeeded, iters_sum], [iters_max]."""
+    v = torch.stack([torch.tensor(status.numel(), dtype=torch.int64, device=status.device),
+                     (status == 0).sum().to(torch.int64), iters.sum().to(torch.int64)])
+    mx = iters.max().to(torch.int64).reshape(1) if iters.numel() else torch.zeros(1, dtype=torch.int64, device=status.device)
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(v, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
+    return v, mx
