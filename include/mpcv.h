@@ -193,6 +193,13 @@ int mpcv_closed_loop(mpcv_handle* h, const double* x_init, const double* pglob,
                      double* out_states, double* out_controls, int32_t* out_steps,
                      int32_t* out_iters, int32_t* out_status, int64_t B, void* stream);
 
+/* Batched exact zero-order hold (replaces mpc.util.c2d, Inverted_pendulum/inverted_pendulum_single_shooting_mpctools.py:24,
+   Trajectory Tracking/Trjectory_tracking_le_LTV.py:126-133, Trajectory_tracking_dynamic_model.py:134):
+   [A Bd; 0 I] = expm([Ac Bc; 0 0] dt) for B systems.  Ac [B x n x n], Bc [B x n x nu] -> A [B x n x n],
+   Bd [B x n x nu], row-major device pointers; n + nu <= 6. */
+int mpcv_c2d(int32_t n, int32_t nu, double dt, const double* Ac, const double* Bc, double* A, double* Bd,
+             int64_t B, void* stream);
+
 /* Measured FP64 FMA peak of the current device in TFLOP/s (register-resident DFMA chains);
    the roofline denominator of bench.py. */
 int mpcv_fp64_peak(double* tflops, double* ms, void* stream);

@@ -8,7 +8,7 @@ from .spec import (WARM_COLD, WARM_REFERENCE, WARM_SHIFT, LAYOUT_AUTO, LAYOUT_TH
 def __getattr__(name):
     # solver.py imports torch and binds the CUDA library; keep `import mpc_verde_b200.spec` light
     import importlib
-    if name in ("nlpsol", "NlpSolver", "fp64_peak"):
+    if name in ("nlpsol", "NlpSolver", "fp64_peak", "c2d"):
         return getattr(importlib.import_module(__name__ + ".solver"), name)
     if name in ("dist", "solver", "mpctools"):
         return importlib.import_module(__name__ + "." + name)

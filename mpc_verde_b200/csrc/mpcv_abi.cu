@@ -55,10 +55,103 @@ __global__ void fp64_peak_kernel(double* out, int iters) {
 }
 
 
+// Exact zero-order hold of xdot = Ac x + Bc u, batched: [A B; 0 I] = expm([Ac Bc; 0 0] dt) — what
+// mpc.util.c2d computes on the host for every scenario / every step of the LTV scripts
+// (Inverted_pendulum/inverted_pendulum_single_shooting_mpctools.py:24, Trjectory_tracking_le_LTV.py:126-133,
+// Trajectory_tracking_dynamic_model.py:134).  One thread per system; scaling and squaring around a
+// degree-18 Taylor polynomial evaluated by Horner's rule (||M / 2^s||_1 <= 1/4, so truncation is far below
+// one ulp; the stiff dynamic bicycle needs s = 9 squarings).
+template <int S>
+__global__ void c2d_kernel(int n, int nu, double dt, const double* Ac, const double* Bc, double* A, double* Bd, long B) {
+  const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double M[S * S], E[S * S], T[S * S];
+#pragma unroll
+  for (int i = 0; i < S * S; ++i) M[i] = 0.0;
+  for (int i = 0; i < n; ++i) {
+    for (int j = 0; j < n; ++j) M[i * S + j] = Ac[(b * n + i) * n + j] * dt;
+    for (int j = 0; j < nu; ++j) M[i * S + n + j] = Bc[(b * n + i) * nu + j] * dt;
+  }
+  double nrm = 0.0;
+#pragma unroll
+  for (int j = 0; j < S; ++j) {
+    double c = 0.0;
+#pragma unroll
+    for (int i = 0; i < S; ++i) c += fabs(M[i * S + j]);
+    nrm = fmax(nrm, c);
+  }
+  int s = 0;
+  while (nrm > 0.25 && s < 60) { nrm *= 0.5; ++s; }
+  const double sc = ldexp(1.0, -s);
+#pragma unroll
+  for (int i = 0; i < S * S; ++i) M[i] *= sc;
+  // Horner: E = I + M (I + M/2 (I + M/3 (... (I + M/18))))
+#pragma unroll
+  for (int i = 0; i < S * S; ++i) E[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < S; ++i) E[i * S + i] = 1.0;
+  for (int k = 18; k >= 1; --k) {
+    const double rk = 1.0 / k;
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+#pragma unroll
+      for (int j = 0; j < S; ++j) {
+        double v = 0.0;
+#pragma unroll
+        for (int l = 0; l < S; ++l) v += M[i * S + l] * E[l * S + j];
+        T[i * S + j] = v * rk;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < S * S; ++i) E[i] = T[i];
+#pragma unroll
+    for (int i = 0; i < S; ++i) E[i * S + i] += 1.0;
+  }
+  for (int q = 0; q < s; ++q) {
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+#pragma unroll
+      for (int j = 0; j < S; ++j) {
+        double v = 0.0;
+#pragma unroll
+        for (int l = 0; l < S; ++l) v += E[i * S + l] * E[l * S + j];
+        T[i * S + j] = v;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < S * S; ++i) E[i] = T[i];
+  }
+  for (int i = 0; i < n; ++i) {
+    for (int j = 0; j < n; ++j) A[(b * n + i) * n + j] = E[i * S + j];
+    for (int j = 0; j < nu; ++j) Bd[(b * n + i) * nu + j] = E[i * S + n + j];
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------
 extern "C" {
+
+int mpcv_c2d(int32_t n, int32_t nu, double dt, const double* Ac, const double* Bc, double* A, double* Bd, int64_t B,
+             void* stream) {
+  if (!Ac || !Bc || !A || !Bd) return mpcv_set_error(-EINVAL, "mpcv_c2d: null argument");
+  if (n < 1 || nu < 1 || n + nu > 6) return mpcv_set_error(-EINVAL, "mpcv_c2d: n + nu must be in 2..6");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return mpcv_set_error(-ENODEV, "no CUDA device");
+  if (B <= 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)((B + 127) / 128);
+  switch (n + nu) {
+    case 2: c2d_kernel<2><<<grid, 128, 0, st>>>(n, nu, dt, Ac, Bc, A, Bd, (long)B); break;
+    case 3: c2d_kernel<3><<<grid, 128, 0, st>>>(n, nu, dt, Ac, Bc, A, Bd, (long)B); break;
+    case 4: c2d_kernel<4><<<grid, 128, 0, st>>>(n, nu, dt, Ac, Bc, A, Bd, (long)B); break;
+    case 5: c2d_kernel<5><<<grid, 128, 0, st>>>(n, nu, dt, Ac, Bc, A, Bd, (long)B); break;
+    default: c2d_kernel<6><<<grid, 128, 0, st>>>(n, nu, dt, Ac, Bc, A, Bd, (long)B); break;
+  }
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 
 const char* mpcv_last_error(void) { return g_last_error.c_str(); }
 

@@ -356,3 +356,26 @@ def fp64_peak(device=None):
         stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
         _lib.check(lib.mpcv_fp64_peak(C.byref(t), C.byref(ms), stream), "mpcv_fp64_peak")
     return t.value, ms.value
+
+
+def c2d(Ac, Bc, dt):
+    """Batched exact zero-order hold on the GPU (`mpc.util.c2d` for B systems at once): Ac [B, n, n],
+    Bc [B, n, nu] (numpy or CUDA tensors) -> (A, Bd) of the same shapes and kind."""
+    on_dev = isinstance(Ac, torch.Tensor) and Ac.is_cuda
+    At = torch.as_tensor(Ac, dtype=torch.float64)
+    Bt = torch.as_tensor(Bc, dtype=torch.float64)
+    unb = At.dim() == 2
+    if unb:
+        At, Bt = At[None], Bt.reshape(1, At.shape[-1], -1)
+    n, nu, B = At.shape[-1], Bt.shape[-1], At.shape[0]
+    dev = At.device if on_dev else torch.device("cuda", torch.cuda.current_device())
+    with torch.cuda.device(dev):
+        Ad, Bd_in = At.to(dev).contiguous(), Bt.to(dev).contiguous()
+        A = torch.empty_like(Ad)
+        Bd = torch.empty_like(Bd_in)
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(_lib.lib().mpcv_c2d(n, nu, float(dt), _ptr(Ad), _ptr(Bd_in), _ptr(A), _ptr(Bd), C.c_int64(B), stream),
+                   "mpcv_c2d")
+    if not on_dev:
+        A, Bd = A.cpu().numpy(), Bd.cpu().numpy()
+    return (A[0], Bd[0]) if unb else (A, Bd)

@@ -439,3 +439,25 @@ def test_max_iter_reported_not_raised(mv):
 def test_fp64_peak_microbenchmark(mv):
     t, ms = mv.fp64_peak()
     assert 5.0 < t < 100.0, t
+
+
+def test_batched_c2d_vs_scipy_and_reference_known_answers(mv):
+    """mpc.util.c2d on the device: pendulum known answers (from invertpend_data_py.xlsx), the
+    stiff dynamic bicycle (eigenvalues down to -1275: h|lambda| = 64) and the lateral-error model, batched."""
+    A, Bd = mv.c2d(problems.PENDULUM_AC, problems.PENDULUM_BC, 0.01)
+    assert np.allclose(Bd[:, 0], [4.83820374e-05, 9.51937011e-03, 9.67801053e-05, 1.90451212e-02], rtol=1e-8)
+    assert abs(A[1, 1] - 0.904806299) < 1e-9 and abs(A[3, 2] - 0.383159406) < 1e-9
+    rng = np.random.default_rng(5)
+    Acs, Bcs = [], []
+    for v in rng.uniform(0.4, 0.8, 300):
+        Ac, Bc = problems.dynamic_bicycle_matrices(v)
+        Acs.append(Ac); Bcs.append(Bc.reshape(4, 1))
+    Ab, Bb = mv.c2d(np.array(Acs), np.array(Bcs), 0.05)
+    for i in range(0, 300, 7):
+        Ar, Br = problems.c2d(Acs[i], Bcs[i], 0.05)
+        assert np.abs(Ab[i] - Ar).max() <= 1e-12 * max(1.0, np.abs(Ar).max())
+        assert np.abs(Bb[i] - Br).max() <= 1e-12 * max(1.0, np.abs(Br).max())
+    Ac3, Bc3 = problems.lateral_error_matrices(0.592)
+    A3, B3 = mv.c2d(Ac3, Bc3, 0.05)
+    Ar, Br = problems.c2d(Ac3, Bc3, 0.05)
+    assert np.abs(A3 - Ar).max() <= 1e-13 and np.abs(B3 - Br).max() <= 1e-13
