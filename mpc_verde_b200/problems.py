@@ -193,3 +193,52 @@ def lateral_error_par(a, b, Nt, Delta, ar=LATERAL_AR, br=LATERAL_BR):
                 p[k, 3] = (((plus - 2 * p[k, 1] + par[1, k, t - 1]) / Delta ** 2) - ar * p[k, 2]) / br
             par[:, k, t] = p[k, :]
     return par
+
+
+def lane_change_extended(a, b, c, v=0.6, dt=0.05):
+    """Reference-path generator Trajectory Tracking/lane_change.py:5-79, as written: the 500-sample lane change
+    (a, b, c) = (x, y, uref) followed by a half turn, a straight, two quarter-radius half turns, a straight back
+    to x = 0 and a closing half turn; `uref` = v on the appended part.  (`np.linspace(..., num=float)` of the
+    script's numpy era truncates: int(k).)  Returns (x_t, y_t, c2) — the columns of `out.csv`."""
+    a, b, c = (np.asarray(q, dtype=np.float64) for q in (a, b, c))
+    k = 500
+    w = np.pi / (k * dt)
+    r = v / w
+    t = np.linspace(1.5 * np.pi, 2.5 * np.pi, k)
+    x_2, y_2 = a[499] + r * np.cos(t), b[499] + r + r * np.sin(t)
+    ds = 10
+    k = ds / (v * dt)
+    t = np.linspace(0, ds, int(k))
+    x_3, y_3 = x_2[-1] - t * v, y_2[-1] + np.zeros(int(k))
+    w = v / (r / 2)
+    k = np.pi / (w * dt)
+    t = np.linspace(np.pi / 2, 1.5 * np.pi, int(k))
+    x_4, y_4 = x_3[-1] + (r / 2) * np.cos(t), y_3[-1] - r / 2 + (r / 2) * np.sin(t)
+    t = np.linspace(np.pi / 2, -np.pi / 2, int(k))
+    x_5, y_5 = x_4[-1] + (r / 2) * np.cos(t), y_4[-1] - 0.5 * r + (r / 2) * np.sin(t)
+    d = x_5[-1]
+    k = d / (v * dt)
+    t = np.linspace(0, k * dt, int(k))
+    x_6, y_6 = d - v * t, y_5[-1] + np.zeros(int(k))
+    r = y_6[-1] / 2
+    w = v / r
+    k = np.pi / (w * dt)
+    t = np.linspace(np.pi / 2, 1.5 * np.pi, int(k))
+    x_7, y_7 = x_6[-1] + r * np.cos(t), y_6[-1] - r + r * np.sin(t)
+    x_t = np.hstack((a, x_2[1:], x_3[1:], x_4[1:], x_5[1:], x_6[1:], x_7[1:]))
+    y_t = np.hstack((b, y_2[1:], y_3[1:], y_4[1:], y_5[1:], y_6[1:], y_7[1:]))
+    c2 = np.zeros(x_t.size)
+    c2[0:500] = c
+    c2[500:] = v
+    return x_t, y_t, c2
+
+
+def circle_reference_par(Nt, Nsim, Delta):
+    """Trajectory Tracking/Trajectory_tracking.py:84-97: per-stage p = (x, y, theta, v, omega) of the unit circle
+    x = cos 0.1 t, y = sin 0.1 t, theta = pi/2 + 0.1 t, v_ref = 1, omega_ref = 1.  Returns par [5, Nt, Nsim]."""
+    par = np.zeros((5, Nt, Nsim))
+    for t in range(Nsim):
+        for k in range(Nt):
+            tt = (t + k) * Delta
+            par[:, k, t] = (np.cos(0.1 * tt), np.sin(0.1 * tt), np.pi / 2 + 0.1 * tt, 1.0, 1.0)
+    return par

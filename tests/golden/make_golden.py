@@ -13,6 +13,7 @@ Sources (reference file -> fixture):
                         (written by Inverted_pendulum/inverted_pendulum_single_shooting_mpctools.py:80-88)
   Trajectory Tracking/dados.csv, dados2.csv (Trajectory Tracking/Phiref.py:379-381)
   Trajectory Tracking/lane_change.csv       (input path of all lane-change scripts)
+  Trajectory Tracking/out.csv               (extended path written by lane_change.py:72-79)
 
 No openpyxl in the image: .xlsx is a zip of XML, parsed by hand.
 """
@@ -88,6 +89,7 @@ def main():
         ("Trajectory Tracking/dados.csv", "lateral_ltv_dados.csv"),
         ("Trajectory Tracking/dados2.csv", "lateral_lti_dados2.csv"),
         ("Trajectory Tracking/lane_change.csv", "lane_change.csv"),
+        ("Trajectory Tracking/out.csv", "lane_change_out.csv"),     # output of the path generator lane_change.py
     ]:
         with open(os.path.join(REF, src)) as f:
             header = f.readline().strip().split(",")

@@ -118,3 +118,15 @@ def test_lateral_error_lti_and_ltv_closed_loops_vs_dados():
     u, x, _ = common.lateral_error_closed_loop(solve, ltv=True)
     assert np.abs(u - g1[:, 3]).max() <= 1e-5
     assert np.abs(x[1:] - g1[:, 0:3]).max() <= 1e-4
+
+
+def test_reference_path_generators():
+    """Host-side reference builders next to the hot path: lane_change.py's extended path is
+    reproduced exactly (its committed output out.csv), the circle builder against its closed form."""
+    g = common.golden("lane_change.csv")
+    o = common.golden("lane_change_out.csv")
+    x, y, c = problems.lane_change_extended(g[:, 0], g[:, 1], g[:, 2])
+    assert x.size == o.shape[0] == 2210
+    assert np.abs(x - o[:, 0]).max() <= 1e-13 and np.abs(y - o[:, 1]).max() <= 1e-13 and np.array_equal(c, o[:, 2])
+    par = problems.circle_reference_par(10, 20, 0.2)
+    assert np.allclose(par[:, 3, 5], [np.cos(0.1 * 1.6), np.sin(0.1 * 1.6), np.pi / 2 + 0.16, 1, 1])
