@@ -110,7 +110,8 @@ struct Layout {
 
 // Relaxed bounds of one variable, precomputed once per kernel (the bounds are shared by the batch).
 struct BndEntry { double lo, hi; int flags, pad; };   // flags: 1 = lower, 2 = upper, 4 = fixed
-constexpr int kStateSlots = 32;
+constexpr int kStateSlots = 40;
+constexpr int kSlotDwHint = 34;   // phase pipeline: delta_w found by the parallel probe (> 0) or -(last delta_w probed)
 constexpr int kRunning = 1000;    // internal "not finished" status
 
 template <class Model, bool SINGLE>
@@ -688,11 +689,13 @@ struct Ipm {
   }
 
   MPCV_DN bool riccati_factor(double dw, bool identity) { return riccati_factor_t<false>(dw, identity, 0, -1); }
+  // inertia probe: the factorisation without any store (only its verdict matters)
+  MPCV_D bool riccati_probe(double dw) { return riccati_factor_t<false, false>(dw, false, 0, -1); }
   // FUSE: the backward VECTOR recursion of riccati_solve(rmode, coff) runs inside the factorisation loop,
   // on the A, B, K, F, P_{k+1} already in registers (the phase pipeline's Riccati kernels are HBM-bound:
   // a separate backward pass re-reads 30 of them per stage).  Same expressions in the same order as
   // riccati_solve; riccati_forward() completes the step.
-  template <bool FUSE>
+  template <bool FUSE, bool STORE = true>
   MPCV_D bool riccati_factor_t(double dw, bool identity, int rmode, int coff) {
     int ok = 1;
     if (g.lane == 0) {
@@ -710,7 +713,7 @@ struct Ipm {
         if (!identity) sigma_r(ix(N, i), &sg, &r);
         Pm[i * NX + i] = (identity ? 1.0 : 0.0) + sg + dw;
       }
-      store_P(N, Pm);
+      if (STORE) store_P(N, Pm);
       FacIn cur;
       for (int k = N - 1; k >= 0 && ok; --k) {
         load_fac(k, identity, cur);
@@ -881,14 +884,16 @@ struct Ipm {
 #pragma unroll
           for (int j = i + 1; j < NX; ++j) Pm[i * NX + j] = Pm[j * NX + i];
         }
-        store_P(k, Pm);
-        const int ro = L.ric + k * NRIC;
+        if (STORE) {
+          store_P(k, Pm);
+          const int ro = L.ric + k * NRIC;
 #pragma unroll
-        for (int i = 0; i < NU * NX; ++i) ws[ro + i] = K[i];
+          for (int i = 0; i < NU * NX; ++i) ws[ro + i] = K[i];
 #pragma unroll
-        for (int i = 0; i < NU; ++i) {
+          for (int i = 0; i < NU; ++i) {
 #pragma unroll
-          for (int j = 0; j <= i; ++j) ws[ro + NU * NX + NU + tri(i, j)] = F[i * NU + j];
+            for (int j = 0; j <= i; ++j) ws[ro + NU * NX + NU + tri(i, j)] = F[i * NU + j];
+          }
         }
       }
     }

@@ -127,17 +127,38 @@ struct Phase {
     return true;
   }
 
-  // inertia-correction retries (IPOPT's delta_w schedule)                       (thread per problem)
+  // IPOPT's delta_w schedule is a deterministic sequence (next_delta_w): attempt `a` of the probe factorises
+  // with its a-th element, WITHOUT stores; the first success of the sequence is what the sequential loop
+  // would have stopped at.                                                      (kProbe lanes per problem)
+  static constexpr int kProbe = 4;
+  MPCV_HD static double probe_dw(const Ipm1& ipm, int a) {
+    double dw = 0.0;
+    for (int i = 0; i <= a; ++i) dw = ipm.next_delta_w(dw);
+    return dw;
+  }
+  MPCV_HD static bool probe_body(const Params& P, const Layout& L, WS ws, const SolveIO& io, const BndEntry* tab,
+                                 int attempt, double* dw_out) {
+    Ipm1 ipm(P, L, ws, Grp<1>(0), io.lbx, io.ubx, tab);
+    ipm.delta_w_last = ws[L.st + 6];
+    const double dw = probe_dw(ipm, attempt);
+    *dw_out = dw;
+    if (dw > 1e20) return false;
+    return ipm.riccati_probe(dw);
+  }
+
+  // inertia-correction retries: factorise with the delta_w the probe found (or walk on through the schedule
+  // when none of the probed values worked), then the vector sweeps              (thread per problem)
   MPCV_HD static void retry_body(const Params& P, const Layout& L, WS ws, const SolveIO& io, long b,
                                  const BndEntry* tab, long long now) {
     Ipm1 ipm(P, L, ws, Grp<1>(0), io.lbx, io.ubx, tab);
     ipm.delta_w_last = ws[L.st + 6];
-    double dw = 0.0;
+    const double hint = ws[L.st + kSlotDwHint];
+    double dw = hint > 0.0 ? hint : (hint < 0.0 ? ipm.next_delta_w(-hint) : ipm.next_delta_w(0.0));
     bool ok = false;
-    while (!ok) {
-      dw = ipm.next_delta_w(dw);
-      if (dw > 1e20) break;
+    while (dw <= 1e20) {
       ok = ipm.template riccati_factor_t<true>(dw, false, 0, L.c);
+      if (ok) break;
+      dw = ipm.next_delta_w(dw);
     }
     if (!ok) {
       ipm.load_state();
@@ -443,6 +464,34 @@ __global__ void __launch_bounds__(kPhaseThreads, 4) ph_factor_kernel(const __gri
       retry = !Phase<Model, WsStrided>::factor_body(a.P, a.L, WsStrided::of(slab, a.L.total, b), io, tab);
     }
     ph_append(retry, b, a.retry, &a.ctrl->n_retry);
+  }
+}
+
+// probe: kProbe lanes per problem of the retry list, each trying one element of the delta_w sequence
+template <class Model>
+__global__ void __launch_bounds__(kPhaseThreads, 4) ph_probe_kernel(const __grid_constant__ PhaseArgs a) {
+  double* const slab = a.slab[ph_cur_after_repack(a.ctrl)];
+  constexpr int NP = Phase<Model, WsStrided>::kProbe;
+  const long n = a.ctrl->n_retry, items = n * NP;
+  if ((long)blockIdx.x * blockDim.x >= items) return;
+  const SolveIO io = *a.io;
+  const BndEntry* tab = ph_bounds_table<Model>(a.P, a.L, io);
+  for (long i0 = (long)blockIdx.x * blockDim.x; i0 < items; i0 += (long)gridDim.x * blockDim.x) {
+    const long it = i0 + threadIdx.x;
+    const int attempt = threadIdx.x & (NP - 1);
+    bool ok = false;
+    double dw = 0.0;
+    WsStrided ws{nullptr};
+    if (it < items) {
+      ws = WsStrided::of(slab, a.L.total, a.retry[it / NP]);
+      ok = Phase<Model, WsStrided>::probe_body(a.P, a.L, ws, io, tab, attempt, &dw);
+    }
+    // first success within the group of NP lanes
+    const unsigned lane = threadIdx.x & 31, gbase = lane & ~(NP - 1);
+    const unsigned m = (__ballot_sync(0xffffffffu, ok) >> gbase) & ((1u << NP) - 1u);
+    const int first = m ? __ffs(m) - 1 : NP - 1;
+    const double dsel = __shfl_sync(0xffffffffu, dw, gbase + first);
+    if (it < items && attempt == 0) ws[a.L.st + kSlotDwHint] = m ? dsel : -dsel;
   }
 }
 

@@ -58,6 +58,16 @@ static int hs_solve_phased_t(const mpcv_spec* s, const SolveIO& io, long B, int*
     }
     for (int e = 0; e < n_act[out]; ++e)                                    // factor
       if (!Ph::factor_body(P, L, ws(act[out][e]), io, tab.data())) retry.push_back(act[out][e]);
+    for (int b : retry) {                                                    // probe (kProbe attempts, no stores)
+      bool found = false;
+      double dsel = 0.0;
+      for (int a = 0; a < Ph::kProbe && !found; ++a) {
+        double dw;
+        found = Ph::probe_body(P, L, ws(b), io, tab.data(), a, &dw);
+        dsel = dw;
+      }
+      ws(b)[L.st + kSlotDwHint] = found ? dsel : -dsel;
+    }
     for (int b : retry) Ph::retry_body(P, L, ws(b), io, b, tab.data(), 0);  // retry
     for (int e = 0; e < n_act[out]; ++e)                                    // post
       if (Ph::running(L, ws(act[out][e]))) Ph::post_body(P, L, ws(act[out][e]), io, tab.data(), g1);
