@@ -146,14 +146,26 @@ struct Phase {
     return ipm.riccati_probe(dw);
   }
 
-  // inertia-correction retries: factorise with the delta_w the probe found (or walk on through the schedule
-  // when none of the probed values worked), then the vector sweeps              (thread per problem)
+  // the probe's winner: the same factorisation with stores + vector sweeps.  Should rounding make it fail
+  // where the store-free probe succeeded, the problem goes to the sequential walk with hint = -dw.
+  MPCV_HD static void apply_body(const Params& P, const Layout& L, WS ws, const SolveIO& io, const BndEntry* tab,
+                                 double dw) {
+    Ipm1 ipm(P, L, ws, Grp<1>(0), io.lbx, io.ubx, tab);
+    if (!ipm.template riccati_factor_t<true>(dw, false, 0, L.c)) { ws[L.st + kSlotDwHint] = -dw; return; }
+    ws[L.st + 6] = dw;
+    ws[L.st + kSlotDwHint] = dw;          // > 0: done, ph_retry_kernel skips it
+    ipm.riccati_forward(L.c);
+  }
+
+  // inertia-correction retries for the problems the probe could not settle: walk on through the schedule
+  // sequentially, then the vector sweeps                                          (thread per problem)
   MPCV_HD static void retry_body(const Params& P, const Layout& L, WS ws, const SolveIO& io, long b,
                                  const BndEntry* tab, long long now) {
     Ipm1 ipm(P, L, ws, Grp<1>(0), io.lbx, io.ubx, tab);
     ipm.delta_w_last = ws[L.st + 6];
     const double hint = ws[L.st + kSlotDwHint];
-    double dw = hint > 0.0 ? hint : (hint < 0.0 ? ipm.next_delta_w(-hint) : ipm.next_delta_w(0.0));
+    if (hint > 0.0) return;               // settled by the probe's winning lane
+    double dw = hint < 0.0 ? ipm.next_delta_w(-hint) : ipm.next_delta_w(0.0);
     bool ok = false;
     while (dw <= 1e20) {
       ok = ipm.template riccati_factor_t<true>(dw, false, 0, L.c);
@@ -427,15 +439,22 @@ __global__ void __launch_bounds__(kPhaseThreads) ph_repack_kernel(const __grid_c
     const int sl = a.act[out][e];
     const double* ps = src + (long)(sl >> 5) * ((long)total * 32) + (sl & 31);
     double* pd = dst + (e >> 5) * ((long)total * 32) + (e & 31);
+    // live after `pre`: everything except the step (d, lam+), the trial residuals, the Riccati factors and
+    // cost-to-go and the per-interval costs, which the rest of the sweep rewrites before reading
+    const Layout& L = a.L;
+    auto dead = [&](int i) {
+      return (i >= L.d && i < L.d + L.n) || (i >= L.qs && i < L.qs + L.N) || (i >= L.lamp && i < L.lamp + L.m) ||
+             (i >= L.ct && i < L.ct + L.m) || i >= L.ric;          // ric and pp are the last two regions
+    };
     int i = 0;
     for (; i + 8 <= total; i += 8) {
       double v[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = ps[(long)(i + j) * 32];
+      for (int j = 0; j < 8; ++j) v[j] = dead(i + j) ? 0.0 : ps[(long)(i + j) * 32];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) pd[(long)(i + j) * 32] = v[j];
+      for (int j = 0; j < 8; ++j) if (!dead(i + j)) pd[(long)(i + j) * 32] = v[j];
     }
-    for (; i < total; ++i) pd[(long)i * 32] = ps[(long)i * 32];
+    for (; i < total; ++i) if (!dead(i)) pd[(long)i * 32] = ps[(long)i * 32];
     a.act[out][e] = (int)e;
   }
 }
@@ -491,7 +510,10 @@ __global__ void __launch_bounds__(kPhaseThreads, 4) ph_probe_kernel(const __grid
     const unsigned m = (__ballot_sync(0xffffffffu, ok) >> gbase) & ((1u << NP) - 1u);
     const int first = m ? __ffs(m) - 1 : NP - 1;
     const double dsel = __shfl_sync(0xffffffffu, dw, gbase + first);
-    if (it < items && attempt == 0) ws[a.L.st + kSlotDwHint] = m ? dsel : -dsel;
+    // the winning lane repeats its factorisation with stores (operands are in L1/L2 now) and runs the vector
+    // sweeps; only when none of the probed values worked the problem is left to ph_retry_kernel
+    if (it < items && m && attempt == first) Phase<Model, WsStrided>::apply_body(a.P, a.L, ws, io, tab, dsel);
+    if (it < items && !m && attempt == 0) ws[a.L.st + kSlotDwHint] = -dsel;
   }
 }
 

@@ -66,7 +66,8 @@ static int hs_solve_phased_t(const mpcv_spec* s, const SolveIO& io, long B, int*
         found = Ph::probe_body(P, L, ws(b), io, tab.data(), a, &dw);
         dsel = dw;
       }
-      ws(b)[L.st + kSlotDwHint] = found ? dsel : -dsel;
+      if (found) Ph::apply_body(P, L, ws(b), io, tab.data(), dsel);     // the winning lane completes the step
+      else ws(b)[L.st + kSlotDwHint] = -dsel;
     }
     for (int b : retry) Ph::retry_body(P, L, ws(b), io, b, tab.data(), 0);  // retry
     for (int e = 0; e < n_act[out]; ++e)                                    // post
