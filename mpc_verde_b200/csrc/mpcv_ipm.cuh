@@ -187,12 +187,17 @@ struct Ipm {
   int nfil, iter;
   // search direction -> line search hand-over
   double ls_alpha_max, ls_theta, ls_gBD, ls_phi;
+  // barrier log-sum of the current iterate = log-sum of the trial point accepted last (same slacks): reused by
+  // direction_post instead of ~2 logs per bounded variable
+  double lg_curr;
+  bool lg_valid;
+  mutable double lg_trial;   // log-sum of the most recent trial evaluation
 
   MPCV_D Ipm(const Params& p, const Layout& l, WS w, Grp<LANES> grp, const double* lb, const double* ub,
              const BndEntry* tab = nullptr)
       : P(p), L(l), ws(w), g(grp), lbx(lb), ubx(ub), btab(tab), N(l.N), ps_base(l.par + NX + Model::NPG),
         df(1.0), mu(0.1), tau(0.99), f_curr(0), theta_max(-1.0), theta_min(-1.0), delta_w_last(0.0), nfil(0),
-        iter(0), ls_alpha_max(1.0), ls_theta(0.0), ls_gBD(0.0), ls_phi(0.0) {}
+        iter(0), ls_alpha_max(1.0), ls_theta(0.0), ls_gBD(0.0), ls_phi(0.0), lg_curr(0.0), lg_valid(false), lg_trial(0.0) {}
 
   // ---- state hand-over between phase kernels ---------------------------------------------------
   MPCV_D void save_state(int status) const {
@@ -202,6 +207,7 @@ struct Ipm {
     ws[o + 4] = theta_max; ws[o + 5] = theta_min; ws[o + 6] = delta_w_last;
     ws[o + 7] = (double)nfil; ws[o + 8] = (double)iter; ws[o + 9] = (double)status;
     ws[o + 10] = ls_alpha_max; ws[o + 11] = ls_theta; ws[o + 12] = ls_gBD; ws[o + 13] = ls_phi;
+    ws[o + 35] = lg_curr; ws[o + 36] = lg_valid ? 1.0 : 0.0;
     for (int q = 0; q < nfil; ++q) { ws[o + 16 + q] = fil_phi[q]; ws[o + 24 + q] = fil_th[q]; }
   }
   MPCV_D int load_state() {
@@ -210,6 +216,7 @@ struct Ipm {
     theta_max = ws[o + 4]; theta_min = ws[o + 5]; delta_w_last = ws[o + 6];
     nfil = (int)ws[o + 7]; iter = (int)ws[o + 8];
     ls_alpha_max = ws[o + 10]; ls_theta = ws[o + 11]; ls_gBD = ws[o + 12]; ls_phi = ws[o + 13];
+    lg_curr = ws[o + 35]; lg_valid = ws[o + 36] != 0.0;
     for (int q = 0; q < nfil; ++q) { fil_phi[q] = ws[o + 16 + q]; fil_th[q] = ws[o + 24 + q]; }
     return (int)ws[o + 9];
   }
@@ -502,6 +509,7 @@ struct Ipm {
     const double f = df * g.sum(fpart);
     const double th = g.sum(thpart);
     double lg = g.sum(logpart);
+    lg_trial = lg;
     const bool anybad = g.max(bad ? 1.0 : 0.0) > 0.0;
     *f_out = f;
     *theta_out = th;
@@ -540,6 +548,7 @@ struct Ipm {
     });
     const double f = sum_stage_costs();
     const double lg = g.sum(logpart);
+    lg_trial = lg;
     const bool anybad = g.max(bad ? 1.0 : 0.0) > 0.0;
     *f_out = f;
     *theta_out = g.sum(thpart);
@@ -1320,6 +1329,7 @@ struct Ipm {
     theta_max = theta_min = -1.0;
     delta_w_last = 0.0;
     iter = 0;
+    lg_valid = false;
   }
 
   // Precondition: eval_derivatives(false) at df = 1.  Gradient-based objective scaling
@@ -1418,13 +1428,17 @@ struct Ipm {
     ls_alpha_max = ftb_primal();
     double theta = 0.0, gBD = 0.0, lg = 0.0;
     lane_loop(L.m, [&](int i) { return V1{ws[L.c + i]}; }, [&](int, const V1& v) { theta += fabs(v.a); });
+    const bool need_lg = !lg_valid;
     lane_loop(L.n, [&](int i) { return V3{ws[L.rb + i], ws[L.d + i], ws[L.w + i]}; }, [&](int i, const V3& v) {
       const Bnd b = bnd(i);
       if (!b.fixed) gBD += v.a * v.b;
-      if (b.hasl) lg += log(v.c - b.lo);
-      if (b.hasu) lg += log(b.hi - v.c);
+      if (need_lg) {
+        if (b.hasl) lg += log(v.c - b.lo);
+        if (b.hasu) lg += log(b.hi - v.c);
+      }
     });
-    theta = g.sum(theta); gBD = g.sum(gBD); lg = g.sum(lg);
+    theta = g.sum(theta); gBD = g.sum(gBD);
+    lg = need_lg ? g.sum(lg) : lg_curr;
     ls_theta = theta;
     ls_gBD = gBD;
     ls_phi = f_curr - mu * lg;
@@ -1490,6 +1504,8 @@ struct Ipm {
     if (!SINGLE)
       lane_loop(L.m, [&](int i) { return V2{ws[L.lam + i], ws[L.lamp + i]}; },
                 [&](int i, const V2& v) { ws[L.lam + i] = v.a + alpha * (v.b - v.a); });
+    lg_curr = lg_trial;          // the accepting trial evaluation was the last one
+    lg_valid = true;
     g.sync();
     sync_blocked();
     ++iter;
@@ -1634,6 +1650,7 @@ struct Ipm {
     }
     const double f = df * g.sum(fpart);
     const double lg = g.sum(logpart);
+    lg_trial = lg;
     const bool anybad = g.max(bad ? 1.0 : 0.0) > 0.0;
     *f_out = f;
     *theta_out = g.sum(thpart);
