@@ -61,7 +61,14 @@ constexpr int kRepackMin = 512;     // do not bother to repack fewer survivors t
 #define MPCV_TAIL_BELOW 4096   /* measured: 512: 24.6 ms, 1024: 24.1, 2048: 23.7, 4096: 23.1, 8192: 23.6, 16384: 24.4, all: 77 */
 #endif
 constexpr int kTailBelow = MPCV_TAIL_BELOW;    // at most this many active problems: leave the sweeps, finish in ph_tail_kernel
-constexpr int kWideBelow = 4096;    // below this many active problems the lane-group kernels use 32 lanes
+#ifndef MPCV_WIDE_BELOW
+#define MPCV_WIDE_BELOW 16384   /* fewer active problems than this: latency-bound, use MPCV_WIDE_LANES lanes per problem */
+#endif
+#ifndef MPCV_WIDE_LANES
+#define MPCV_WIDE_LANES 8   /* C4 (4,096 scenarios x 100 steps): 4 lanes 354 ms, 8 lanes 299 ms, 32 lanes 426 ms */
+#endif
+constexpr int kWideBelow = MPCV_WIDE_BELOW;
+constexpr int kWideLanes = MPCV_WIDE_LANES;    // below this many active problems the lane-group kernels use 32 lanes
 
 template <class Model, class WS, int LANES = 1>
 struct Phase {
@@ -300,10 +307,10 @@ struct PhaseArgs {
 
 constexpr int kPhaseThreads = 128;       // thread-per-problem / thread-per-interval kernels
 #ifndef MPCV_GROUP_THREADS
-#define MPCV_GROUP_THREADS 256
+#define MPCV_GROUP_THREADS 128
 #endif
 #ifndef MPCV_GROUP_LANES
-#define MPCV_GROUP_LANES 8
+#define MPCV_GROUP_LANES 4   /* measured: 16 lanes 33.6 ms, 8: 28.2, 4: 27.5 (r1b); 8 -> 4 again 21.7 -> 21.3 ms (r1c) */
 #endif
 #ifndef MPCV_REPACK_NUM
 #define MPCV_REPACK_NUM 7   /* repack when n_active * DEN <= slots * NUM (1/2: 30.3 ms, 3/4: 28.2, 7/8: 27.6) */
@@ -312,12 +319,12 @@ constexpr int kPhaseThreads = 128;       // thread-per-problem / thread-per-inte
 #define MPCV_REPACK_DEN 8
 #endif
 constexpr int kWarpPhaseThreads = MPCV_GROUP_THREADS;   // lane-group kernels
-// pre / post / accept: 8 lanes per problem, the 4 problems of a warp being neighbours in the active list.
-// Scalar work (pow, filter logic, state hand-over) is then shared by 4 problems per warp instruction, and
-// a warp-load touches 8 whole sectors: the 4 neighbouring problems share each 32-byte sector of the slab.
+// pre / post / accept: kGroupLanes lanes per problem, the problems of a warp being neighbours in the active list.
+// Scalar work (pow, filter logic, state hand-over) is then shared by 32 / kGroupLanes problems per warp
+// instruction, and a warp-load touches whole sectors: neighbouring problems share each 32-byte sector of the slab.
 constexpr int kGroupLanes = MPCV_GROUP_LANES;
 #ifndef MPCV_GROUP_MINB
-#define MPCV_GROUP_MINB 4   /* 64 registers: measured best on B200 (2: 29.6 ms, 3: 28.2 ms, 4: 27.3 ms per batch) */
+#define MPCV_GROUP_MINB 8   /* 64 registers at 128 threads: measured best on B200 (128 regs: 29.6 ms, 85: 28.2, 64: 27.3 per batch) */
 #endif
 
 // Every phase kernel is launched with a FIXED grid (the launches are nodes of a CUDA graph) sized to
@@ -412,10 +419,10 @@ __global__ void __launch_bounds__(kWarpPhaseThreads, MPCV_GROUP_MINB) ph_pre_ker
   const int in = a.ctrl->sweep & 1, out = in ^ 1;
   const int n_in = a.ctrl->n_act[in];
   const bool wide = n_in < kWideBelow;
-  if ((long)blockIdx.x * (kWarpPhaseThreads / (wide ? 32 : kGroupLanes)) >= n_in) return;
+  if ((long)blockIdx.x * (kWarpPhaseThreads / (wide ? kWideLanes : kGroupLanes)) >= n_in) return;
   const SolveIO io = *a.io;
   const BndEntry* tab = ph_bounds_table<Model>(a.P, a.L, io);
-  if (wide) ph_pre_run<Model, 32>(a, slab, io, tab, in, out, n_in, keep_s, b_s, &base_s);
+  if (wide) ph_pre_run<Model, kWideLanes>(a, slab, io, tab, in, out, n_in, keep_s, b_s, &base_s);
   else ph_pre_run<Model, kGroupLanes>(a, slab, io, tab, in, out, n_in, keep_s, b_s, &base_s);
 }
 
@@ -550,10 +557,10 @@ __global__ void __launch_bounds__(kWarpPhaseThreads, MPCV_GROUP_MINB) ph_post_ke
   const int out = (a.ctrl->sweep & 1) ^ 1;
   const int n = a.ctrl->n_act[out];
   const bool wide = n < kWideBelow;
-  if ((long)blockIdx.x * (kWarpPhaseThreads / (wide ? 32 : kGroupLanes)) >= n) return;
+  if ((long)blockIdx.x * (kWarpPhaseThreads / (wide ? kWideLanes : kGroupLanes)) >= n) return;
   const SolveIO io = *a.io;
   const BndEntry* tab = ph_bounds_table<Model>(a.P, a.L, io);
-  if (wide) ph_post_run<Model, 32>(a, slab, io, tab, out, n);
+  if (wide) ph_post_run<Model, kWideLanes>(a, slab, io, tab, out, n);
   else ph_post_run<Model, kGroupLanes>(a, slab, io, tab, out, n);
 }
 
@@ -594,10 +601,10 @@ __global__ void __launch_bounds__(kWarpPhaseThreads, MPCV_GROUP_MINB) ph_accept_
   const int out = (a.ctrl->sweep & 1) ^ 1;
   const int n = a.ctrl->n_act[out];
   const bool wide = n < kWideBelow;
-  if ((long)blockIdx.x * (kWarpPhaseThreads / (wide ? 32 : kGroupLanes)) >= n) return;
+  if ((long)blockIdx.x * (kWarpPhaseThreads / (wide ? kWideLanes : kGroupLanes)) >= n) return;
   const SolveIO io = *a.io;
   const BndEntry* tab = ph_bounds_table<Model>(a.P, a.L, io);
-  if (wide) ph_accept_run<Model, 32>(a, slab, io, tab, out, n);
+  if (wide) ph_accept_run<Model, kWideLanes>(a, slab, io, tab, out, n);
   else ph_accept_run<Model, kGroupLanes>(a, slab, io, tab, out, n);
 }
 
@@ -653,6 +660,13 @@ __global__ void __launch_bounds__(kWarpPhaseThreads) ph_tail_kernel(const __grid
   }
 }
 
+// hand-off threshold: 1/16 of the batch, at most kTailBelow (a small batch would otherwise run entirely in the
+// tail kernel, which is ~3x less efficient per iteration than the sweeps)
+__host__ __device__ inline int ph_tail_below(int B) {
+  const int t = B >> 4;
+  return t < 32 ? 32 : (t > kTailBelow ? kTailBelow : t);
+}
+
 // end of an iteration sweep: swap the lists and tell the WHILE node whether anyone is left
 static __global__ void ph_flip_kernel(PhaseCtrl* ctrl, cudaGraphConditionalHandle handle, int use_handle) {
   const int in = ctrl->sweep & 1, out = in ^ 1;
@@ -667,7 +681,7 @@ static __global__ void ph_flip_kernel(PhaseCtrl* ctrl, cudaGraphConditionalHandl
   ctrl->sweep += 1;
   ctrl->sweeps_total += 1;
   ctrl->sweeps_cum += 1;
-  if (use_handle) cudaGraphSetConditional(handle, ctrl->n_act[out] > kTailBelow ? 1u : 0u);
+  if (use_handle) cudaGraphSetConditional(handle, ctrl->n_act[out] > ph_tail_below(ctrl->B) ? 1u : 0u);
 }
 
 static __global__ void ph_begin_kernel(PhaseCtrl* ctrl, SolveIO* dst, const SolveIO io, int B) {

@@ -244,7 +244,7 @@ static int phase_host_loop(mpcv_handle* h, cudaStream_t st) {
     }
     CUDA_OK(cudaMemcpyAsync(s->h_ctrl, s->ctrl, sizeof(PhaseCtrl), cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
-    if (s->h_ctrl->n_act[s->h_ctrl->sweep & 1] <= kTailBelow) break;
+    if (s->h_ctrl->n_act[s->h_ctrl->sweep & 1] <= ph_tail_below(s->h_ctrl->B)) break;
   }
   ph_tail_kernel<Model><<<gr.warp, kWarpPhaseThreads, smem, st>>>(a);
   h->launches++;
