@@ -160,6 +160,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # (NCCL channel caps were tried for the side-stream gather: NCCL_MAX_NCHANNELS=4 helps at N=2,
+        # 21.8 vs 24.4 ms/step, but hurts at N=8, 27.1 vs 24.0 — the defaults stay.)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     prob = problems.unicycle_multiple_shooting()
