@@ -17,20 +17,25 @@
 // problem b at slab[(b/32)*32*total + i*32 + b%32]); the scalar state of a solve (mu, tau, filter, ...) is parked in
 // ws[L.st ..] between launches.
 //
-// One interior-point iteration = pre -> repack -> factor -> retry -> post -> trial -> accept -> slow -> der -> flip:
-//   pre     8 lanes / problem     error measures, convergence test (exports finished problems), barrier
+// One interior-point iteration = pre -> repack -> factor -> probe -> retry -> post -> trial -> accept -> slow -> der -> flip:
+//   pre     lane group / problem  error measures, convergence test (exports finished problems), barrier
 //                                 update, Sigma / barrier gradient; ordered compaction of the active list
-//   repack  thread per problem    (when a quarter of the slots have emptied) dense copy of the survivors
+//   repack  thread per problem    (when an eighth of the slots have emptied) dense copy of the survivors
 //   factor  thread per problem    Riccati factorisation with delta_w = 0 + vector recursions
-//   retry   thread per problem    IPOPT's delta_w schedule, only over the problems with wrong inertia
-//   post    8 lanes / problem     fraction-to-the-boundary step, merit-function terms
+//   probe   4 lanes / problem     the next four values of IPOPT's delta_w sequence tried at once; the first
+//                                 success completes the step (only over the problems with wrong inertia)
+//   retry   thread per problem    sequential walk through the rest of the sequence (rarely anything left)
+//   post    lane group / problem  fraction-to-the-boundary step, merit-function terms
 //   trial   thread per (problem, interval)   first line-search trial point
-//   accept  8 lanes / problem     filter test of the full step, dual step, update of (w, z, lambda)
+//   accept  lane group / problem  filter test of the full step, dual step, update of (w, z, lambda)
 //   slow    warp per problem      backtracking / second-order correction, only over rejected problems
 //   der     thread per (problem, interval)   derivative sweep at the new iterate
-//   flip    one thread            list swap, loop condition of the WHILE node
+//   flip    one thread            list swap, repack commit, loop condition of the WHILE node
+// then ph_tail_kernel: once at most min(4096, B/16) problems are active the loop ends and the stragglers
+// finish one warp per problem, every phase in-kernel.
+// A lane group is kGroupLanes = 4 lanes (kWideLanes = 8 below kWideBelow active problems).
 // The sequential recursions run one thread per problem (every lane busy, coalesced rows of the blocked
-// slab); everything that is parallel over variables or intervals runs with 32x or 10x more threads so
+// slab); everything that is parallel over variables or intervals runs with 4-10x more threads so
 // that HBM latency is hidden by parallelism instead of being serialised inside one thread.
 // The whole solve is ONE CUDA graph whose iteration body sits in a conditional WHILE node, so
 // mpcv_solve stays asynchronous on the caller's stream (no host round trip per iteration).
@@ -45,7 +50,7 @@ namespace mpcv {
 
 struct PhaseCtrl {
   int n_act[2];   // entries of the two ping-pong active lists
-  int sweep;      // iteration sweeps done; list (sweep & 1) is the input of the next newton phase
+  int sweep;      // iteration sweeps done; list (sweep & 1) is the input of the next `pre` phase
   int B;          // problems of this call
   int sweeps_total;
   int n_retry;    // problems whose first factorisation had the wrong inertia (this sweep)
@@ -68,7 +73,7 @@ constexpr int kTailBelow = MPCV_TAIL_BELOW;    // at most this many active probl
 #define MPCV_WIDE_LANES 8   /* C4 (4,096 scenarios x 100 steps): 4 lanes 354 ms, 8 lanes 299 ms, 32 lanes 426 ms */
 #endif
 constexpr int kWideBelow = MPCV_WIDE_BELOW;
-constexpr int kWideLanes = MPCV_WIDE_LANES;    // below this many active problems the lane-group kernels use 32 lanes
+constexpr int kWideLanes = MPCV_WIDE_LANES;    // lanes per problem of the lane-group kernels below kWideBelow active problems
 
 template <class Model, class WS, int LANES = 1>
 struct Phase {
