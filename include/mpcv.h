@@ -210,11 +210,11 @@ int mpcv_fp64_peak(double* tflops, double* ms, void* stream);
 int mpcv_set_latency_buffer(mpcv_handle* h, long long* dev_ns);
 
 /* number of kernel launches issued through this handle since creation (for the phased layout the
-   iteration sweeps run inside a CUDA graph: 11 kernel nodes per sweep, see mpcv_phase_sweeps) */
+   iteration sweeps run inside a CUDA graph: 12 kernel nodes per sweep, see mpcv_phase_sweeps) */
 int64_t mpcv_launch_count(const mpcv_handle* h);
 
 /* phased layout (synchronises `stream`): interior-point sweeps executed by the last mpcv_solve, and the
-   number of kernels run through this handle since creation INCLUDING the 11 kernel nodes of every
+   number of kernels run through this handle since creation INCLUDING the 12 kernel nodes of every
    graph-driven sweep (which mpcv_launch_count cannot see from the host).  Either out may be NULL. */
 int mpcv_phase_sweeps(mpcv_handle* h, int32_t* sweeps, int64_t* kernel_nodes, void* stream);
 

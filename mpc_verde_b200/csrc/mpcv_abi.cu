@@ -226,8 +226,8 @@ int mpcv_phase_sweeps(mpcv_handle* h, int32_t* sweeps, int64_t* kernel_nodes, vo
   int n = 0, cum = 0;
   if (int rc = mpcv_phase_vtable_of(h->spec.model)->sweeps(h, (cudaStream_t)stream, &n, &cum)) return rc;
   if (sweeps) *sweeps = n;
-  // launches issued from the host + 11 kernel nodes per graph-driven sweep
-  if (kernel_nodes) *kernel_nodes = h->launches + (h->phase_graph_launches > 0 ? 11 * (int64_t)cum : 0);
+  // launches issued from the host + 12 kernel nodes per graph-driven sweep
+  if (kernel_nodes) *kernel_nodes = h->launches + (h->phase_graph_launches > 0 ? 12 * (int64_t)cum : 0);
   return 0;
 }
 

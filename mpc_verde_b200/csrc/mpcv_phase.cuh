@@ -62,6 +62,10 @@ struct PhaseCtrl {
   int pad;
 };
 constexpr int kRepackMin = 512;     // do not bother to repack fewer survivors than this
+#ifndef MPCV_REPACK_SPLIT
+#define MPCV_REPACK_SPLIT 4
+#endif
+constexpr int kRepackSplit = MPCV_REPACK_SPLIT;
 #ifndef MPCV_TAIL_BELOW
 #define MPCV_TAIL_BELOW 4096   /* measured: 512: 24.6 ms, 1024: 24.1, 2048: 23.7, 4096: 23.1, 8192: 23.6, 16384: 24.4, all: 77 */
 #endif
@@ -447,28 +451,41 @@ __global__ void __launch_bounds__(kPhaseThreads) ph_repack_kernel(const __grid_c
   const double* src = a.slab[a.ctrl->cur];
   double* dst = a.slab[a.ctrl->cur ^ 1];
   const int total = a.L.total;
-  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) {
+  // kRepackSplit threads per survivor, each copying an interleaved share of the elements (the copy is latency-
+  // bound: more threads in flight, same bytes)
+  const long items = (long)n * kRepackSplit;
+  for (long it = (long)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (long)gridDim.x * blockDim.x) {
+    const long e = it % n;                      // a warp copies the same share of 32 neighbouring survivors
+    const int part = (int)(it / n);
     const int sl = a.act[out][e];
     const double* ps = src + (long)(sl >> 5) * ((long)total * 32) + (sl & 31);
     double* pd = dst + (e >> 5) * ((long)total * 32) + (e & 31);
     // live after `pre`: everything except the step (d, lam+), the trial residuals, the Riccati factors and
     // cost-to-go and the per-interval costs, which the rest of the sweep rewrites before reading
     const Layout& L = a.L;
-    auto dead = [&](int i) {
-      return (i >= L.d && i < L.d + L.n) || (i >= L.qs && i < L.qs + L.N) || (i >= L.lamp && i < L.lamp + L.m) ||
-             (i >= L.ct && i < L.ct + L.m) || i >= L.ric;          // ric and pp are the last two regions
+    auto live = [&](int i) {
+      return i < total && !((i >= L.d && i < L.d + L.n) || (i >= L.qs && i < L.qs + L.N) ||
+                            (i >= L.lamp && i < L.lamp + L.m) || (i >= L.ct && i < L.ct + L.m) ||
+                            i >= L.ric);          // ric and pp are the last two regions
     };
-    int i = 0;
-    for (; i + 8 <= total; i += 8) {
+    const int nchunks = (total + 7) / 8;
+    for (int c = part; c < nchunks; c += kRepackSplit) {
       double v[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = dead(i + j) ? 0.0 : ps[(long)(i + j) * 32];
+      for (int j = 0; j < 8; ++j) v[j] = live(c * 8 + j) ? ps[(long)(c * 8 + j) * 32] : 0.0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) if (!dead(i + j)) pd[(long)(i + j) * 32] = v[j];
+      for (int j = 0; j < 8; ++j) if (live(c * 8 + j)) pd[(long)(c * 8 + j) * 32] = v[j];
     }
-    for (; i < total; ++i) if (!dead(i)) pd[(long)i * 32] = ps[(long)i * 32];
-    a.act[out][e] = (int)e;
   }
+}
+
+// after the copy (all threads of ph_repack_kernel are done): the list becomes the identity
+template <class Model>
+__global__ void ph_repack_list_kernel(const __grid_constant__ PhaseArgs a) {
+  const int out = (a.ctrl->sweep & 1) ^ 1;
+  const int n = a.ctrl->n_act[out];
+  if (!ph_repack_wanted(a.ctrl, n)) return;
+  for (long e = (long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) a.act[out][e] = (int)e;
 }
 
 // slab index for the kernels that run after the repack of the current sweep (the decision is a pure
@@ -649,8 +666,11 @@ __global__ void __launch_bounds__(kPhaseThreads) ph_der_kernel(const __grid_cons
 // mean iteration count) finish here, one warp per problem, every phase in-kernel.  A sweep over so few
 // problems is pure launch-plus-latency floor (~200 us for 10 dependent launches); in here an iteration costs
 // what its own dependent chain costs and problems do not wait for each other.
+#ifndef MPCV_TAIL_MINB
+#define MPCV_TAIL_MINB 1
+#endif
 template <class Model>
-__global__ void __launch_bounds__(kWarpPhaseThreads) ph_tail_kernel(const __grid_constant__ PhaseArgs a) {
+__global__ void __launch_bounds__(kWarpPhaseThreads, MPCV_TAIL_MINB) ph_tail_kernel(const __grid_constant__ PhaseArgs a) {
   double* const slab = a.slab[a.ctrl->cur];
   const int in = a.ctrl->sweep & 1;
   const int n = a.ctrl->n_act[in];

@@ -187,11 +187,12 @@ static int phase_build_graph(mpcv_handle* h) {
   cp.conditional.size = 1;
   CUDA_OK(cudaGraphAddNode(&n_while, g, &n_der1, 1, &cp));
   cudaGraph_t body = cp.conditional.phGraph_out[0];
-  cudaGraphNode_t b_probe, b_pre, b_repack, b_factor, b_retry, b_post, b_trial, b_accept, b_slow, b_der, b_flip;
+  cudaGraphNode_t b_probe, b_pre, b_repack, b_relist, b_factor, b_retry, b_post, b_trial, b_accept, b_slow, b_der, b_flip;
   void* a_flip[] = {&s->ctrl, &handle, &use_handle};
   if (int rc = add_kernel(body, &b_pre, nullptr, (void*)ph_pre_kernel<Model>, gr.group, kWarpPhaseThreads, smem, a_init)) return rc;
   if (int rc = add_kernel(body, &b_repack, &b_pre, (void*)ph_repack_kernel<Model>, gr.prob, kPhaseThreads, 0, a_init)) return rc;
-  if (int rc = add_kernel(body, &b_factor, &b_repack, (void*)ph_factor_kernel<Model>, gr.prob, kPhaseThreads, smem, a_init)) return rc;
+  if (int rc = add_kernel(body, &b_relist, &b_repack, (void*)ph_repack_list_kernel<Model>, gr.prob, kPhaseThreads, 0, a_init)) return rc;
+  if (int rc = add_kernel(body, &b_factor, &b_relist, (void*)ph_factor_kernel<Model>, gr.prob, kPhaseThreads, smem, a_init)) return rc;
   if (int rc = add_kernel(body, &b_probe, &b_factor, (void*)ph_probe_kernel<Model>, gr.prob, kPhaseThreads, smem, a_init)) return rc;
   if (int rc = add_kernel(body, &b_retry, &b_probe, (void*)ph_retry_kernel<Model>, gr.prob, kPhaseThreads, smem, a_init)) return rc;
   if (int rc = add_kernel(body, &b_post, &b_retry, (void*)ph_post_kernel<Model>, gr.group, kWarpPhaseThreads, smem, a_init)) return rc;
@@ -231,6 +232,7 @@ static int phase_host_loop(mpcv_handle* h, cudaStream_t st) {
     for (int c = 0; c < chunk; ++c) {
       ph_pre_kernel<Model><<<gr.group, kWarpPhaseThreads, smem, st>>>(a);
       ph_repack_kernel<Model><<<gr.prob, kPhaseThreads, 0, st>>>(a);
+      ph_repack_list_kernel<Model><<<gr.prob, kPhaseThreads, 0, st>>>(a);
       ph_factor_kernel<Model><<<gr.prob, kPhaseThreads, smem, st>>>(a);
       ph_probe_kernel<Model><<<gr.prob, kPhaseThreads, smem, st>>>(a);
       ph_retry_kernel<Model><<<gr.prob, kPhaseThreads, smem, st>>>(a);
@@ -240,7 +242,7 @@ static int phase_host_loop(mpcv_handle* h, cudaStream_t st) {
       ph_slow_kernel<Model><<<gr.warp, kWarpPhaseThreads, smem, st>>>(a);
       ph_der_kernel<Model><<<gr.stage, kPhaseThreads, smem, st>>>(a);
       ph_flip_kernel<<<1, 1, 0, st>>>(s->ctrl, none, 0);
-      h->launches += 11;
+      h->launches += 12;
     }
     CUDA_OK(cudaMemcpyAsync(s->h_ctrl, s->ctrl, sizeof(PhaseCtrl), cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));

@@ -93,7 +93,7 @@ class NlpSolver:
         return int(n.value), int(k.value)
 
     def phase_sweeps(self):
-        """Interior-point sweeps the last phased-layout solve ran on the device (each sweep is eleven
+        """Interior-point sweeps the last phased-layout solve ran on the device (each sweep is twelve
         kernel nodes of the solve's CUDA graph).  Synchronises the current stream."""
         return self._phase_counts()[0]
 
