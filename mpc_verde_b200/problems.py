@@ -242,3 +242,34 @@ def circle_reference_par(Nt, Nsim, Delta):
             tt = (t + k) * Delta
             par[:, k, t] = (np.cos(0.1 * tt), np.sin(0.1 * tt), np.pi / 2 + 0.1 * tt, 1.0, 1.0)
     return par
+
+
+def frenet_reference_par(xtraj, ytraj, vdes, Nt, Delta, t):
+    """Per-stage parameters of Trajectory Tracking/test2.py:79-100 at MPC step t, as written: p[k] =
+    (y_ref, phi_ref, p2, p3) with p2 = vdes and p3 = ||(xdd, ydd)|| from central differences — which the cost
+    and the model then unpack as (kappat, vdes) = (p[2], p[3]): swapped, and kept that way.  Returns p [Nt, 4]."""
+    xtraj, ytraj, vdes = (np.asarray(q, dtype=np.float64) for q in (xtraj, ytraj, vdes))
+    Nsim = 500                                   # test2.py:61 (the builder indexes against it)
+    p = np.zeros((Nt, 4))
+    for k in range(Nt):
+        if t + k > Nsim - 1:
+            p[k, 0] = ytraj[Nsim - 1]
+            p[k, 1] = np.arctan2(ytraj[Nsim - 1] - ytraj[Nsim - 2], xtraj[Nsim - 1] - xtraj[Nsim - 2])
+        elif t + k == 0:
+            p[k, 0] = ytraj[k + t]
+            p[k, 1] = 0.0
+        else:
+            p[k, 0] = ytraj[k + t]
+            p[k, 1] = np.arctan2(ytraj[k + t] - ytraj[k + t - 1], xtraj[k + t] - xtraj[k + t - 1])
+        if t + k < 2:
+            p[k, 3] = 1.0
+            p[k, 2] = vdes[t + k]
+        elif t + k > Nsim - 2:
+            p[k, 3] = p[k - 1, 3]
+            p[k, 2] = vdes[Nsim - 1]
+        else:
+            ddx = (xtraj[k + t - 1] - 2 * xtraj[k + t] + xtraj[k + t + 1]) / Delta ** 2
+            ddy = (ytraj[k + t - 1] - 2 * ytraj[k + t] + ytraj[k + t + 1]) / Delta ** 2
+            p[k, 3] = np.hypot(ddx, ddy)
+            p[k, 2] = vdes[t + k]
+    return p

@@ -130,3 +130,21 @@ def test_reference_path_generators():
     assert np.abs(x - o[:, 0]).max() <= 1e-13 and np.abs(y - o[:, 1]).max() <= 1e-13 and np.array_equal(c, o[:, 2])
     par = problems.circle_reference_par(10, 20, 0.2)
     assert np.allclose(par[:, 3, 5], [np.cos(0.1 * 1.6), np.sin(0.1 * 1.6), np.pi / 2 + 0.16, 1, 1])
+
+
+def test_result_sinks_and_error_log():
+    """The table the unicycle scripts dump, rebuilt from closed_loop-shaped arrays, equals 1exemplo.xlsx; the
+    LTV tracker's error log runs on the dados.csv loop; the test2.py builder keeps its swapped entries."""
+    from mpc_verde_b200 import sinks
+    g = common.golden("unicycle_ms_1exemplo.csv")
+    states, controls = g[1:, 0:3], g[:84, 3:5]            # what closed_loop returns for this run (84 MPC steps)
+    tab = sinks.unicycle_table(np.vstack([states[0:1], g[2:, 0:3], g[-1:, 0:3]]), controls, 0.2, 84)
+    assert tab.shape == (85, 6)
+    assert np.abs(tab[:, 0:5] - g[:, 0:5]).max() <= 1e-15 and np.abs(tab[:, 5] - g[:, 5]).max() <= 1e-9
+    solve = lambda sp, w0, lbx, ubx, p: O.solve(sp, w0, lbx, ubx, p)["x"]
+    u, x, par = common.lateral_error_closed_loop(solve, ltv=True, nsim=120)
+    lc = common.golden("lane_change.csv")
+    e = sinks.lateral_tracking_errors(x, u, par, lc[:, 0], lc[:, 1], lc[:, 2], 0.05)
+    assert e["path"].shape == (2, 120) and 0 <= e["mse"] < 5 and e["max"] >= e["dist"] > 0
+    p = problems.frenet_reference_par(lc[:, 0], lc[:, 1], lc[:, 2], 20, 0.05, t=10)
+    assert p.shape == (20, 4) and np.allclose(p[:, 2], lc[10:30, 2]) and np.all(p[:, 3] >= 0)
