@@ -14,22 +14,46 @@ using namespace mpcv;
 #endif
 #include "mpcv_model_select.h"
 
-struct mpcv_phase_state {
+// One pipe = one independent instance of the pipeline (lists, control block, graph) over a contiguous share of
+// the batch, launched on its own stream.  The sweeps are batch-synchronous, so a single pipe leaves the GPU
+// waiting at every launch boundary and, late in the solve, at the latency floor of each phase; with several
+// pipes in flight a memory-bound phase of one share overlaps the FP64-bound derivative sweep or a floor-bound
+// launch of another.  MPCV_PHASE_PIPES (1..kMaxPipes) overrides the choice.
+constexpr int kMaxPipes = 8;
+#ifndef MPCV_PIPES_DEFAULT
+#define MPCV_PIPES_DEFAULT 4   /* C2, B = 65,536 on B200: 1 pipe 20.4 ms, 2: 19.3, 3: 18.8, 4: 18.7, 8: 25.1 */
+#endif
+#ifndef MPCV_PIPE_MIN
+#define MPCV_PIPE_MIN 16384    /* do not split below this many problems per pipe (8 x 8,192 is slower than one pipe) */
+#endif
+struct PhasePipe {
   int* act[2] = {nullptr, nullptr};
   int* retry = nullptr;
   int* slow = nullptr;
+  double* slab[2] = {nullptr, nullptr};
+  PhaseCtrl* ctrl = nullptr;
+  SolveIO* d_io = nullptr;
+  PhaseCtrl* h_ctrl = nullptr;      // pinned mirror (host-loop mode, sweep accounting)
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  cudaStream_t stream = nullptr;    // pipes 1.. run on their own stream, forked from / joined to the caller's
+  cudaEvent_t done = nullptr;
+};
+struct mpcv_phase_state {
+  PhasePipe pipe[kMaxPipes];
+  int npipes = 0;                   // pipes the lists / graphs are laid out for
+  int* lists = nullptr;             // one allocation: 4 lists x npipes x cap
+  PhaseCtrl* ctrl = nullptr;        // [kMaxPipes]
+  SolveIO* d_io = nullptr;          // [kMaxPipes]
+  PhaseCtrl* h_ctrl = nullptr;      // [kMaxPipes] pinned
+  cudaEvent_t fork = nullptr;
   double* slab2 = nullptr;          // second workspace slab (repack target)
   LoopBufs lb = {};                 // closed-loop driver buffers
   long lb_cap = 0;
   size_t slab2_doubles = 0;
-  PhaseCtrl* ctrl = nullptr;
-  SolveIO* d_io = nullptr;
-  PhaseCtrl* h_ctrl = nullptr;      // pinned mirror (host-loop mode)
-  long cap = 0;                     // problems the lists / grids are sized for
-  cudaGraph_t graph = nullptr;
-  cudaGraphExec_t exec = nullptr;
+  long cap = 0;                     // problems PER PIPE the lists / grids are sized for
   bool graph_failed = false;
-  double* graph_slab = nullptr;     // the graph bakes these in: rebuild when they change
+  double* graph_slab = nullptr;     // the graphs bake these in: rebuild when they change
   long graph_stride = 0;
 };
 
@@ -41,14 +65,22 @@ static void loop_free(mpcv_phase_state* s) {
   s->lb_cap = 0;
 }
 
+static void phase_drop_graphs(mpcv_phase_state* s) {
+  for (PhasePipe& q : s->pipe) {
+    if (q.exec) { cudaGraphExecDestroy(q.exec); q.exec = nullptr; }
+    if (q.graph) { cudaGraphDestroy(q.graph); q.graph = nullptr; }
+  }
+}
+
 static void phase_free(mpcv_phase_state* s) {
   if (!s) return;
-  if (s->exec) cudaGraphExecDestroy(s->exec);
-  if (s->graph) cudaGraphDestroy(s->graph);
-  if (s->act[0]) cudaFree(s->act[0]);
-  if (s->act[1]) cudaFree(s->act[1]);
-  if (s->retry) cudaFree(s->retry);
-  if (s->slow) cudaFree(s->slow);
+  phase_drop_graphs(s);
+  for (PhasePipe& q : s->pipe) {
+    if (q.stream) cudaStreamDestroy(q.stream);
+    if (q.done) cudaEventDestroy(q.done);
+  }
+  if (s->fork) cudaEventDestroy(s->fork);
+  if (s->lists) cudaFree(s->lists);
   if (s->slab2) cudaFree(s->slab2);
   loop_free(s);
   if (s->ctrl) cudaFree(s->ctrl);
@@ -57,44 +89,66 @@ static void phase_free(mpcv_phase_state* s) {
   delete s;
 }
 
-static int phase_ensure(mpcv_handle* h, long B) {
+// pipes for a batch of B problems
+static int phase_pipes_for(long B) {
+  int k = MPCV_PIPES_DEFAULT;
+  if (const char* env = getenv("MPCV_PHASE_PIPES")) { const int v = atoi(env); if (v >= 1) k = v; }
+  if (const char* env = getenv("MPCV_PHASE_HOSTLOOP")) if (env[0] == '1') k = 1;   // the host loop synchronises: one pipe
+  if (k > kMaxPipes) k = kMaxPipes;
+  long min_share = MPCV_PIPE_MIN;
+  if (const char* env = getenv("MPCV_PHASE_PIPE_MIN")) { const long v = atol(env); if (v >= 32) min_share = v; }
+  while (k > 1 && B / k < min_share) --k;
+  return k;
+}
+
+static int phase_ensure(mpcv_handle* h, long B, int K) {
   if (!h->phase) h->phase = new mpcv_phase_state();
   mpcv_phase_state* s = h->phase;
   if (!s->ctrl) {
-    CUDA_OK(cudaMalloc(&s->ctrl, sizeof(PhaseCtrl)));
+    CUDA_OK(cudaMalloc(&s->ctrl, kMaxPipes * sizeof(PhaseCtrl)));
     // the memset runs on the legacy default stream, which does NOT order against non-blocking streams:
     // wait for it, or it can land after the first ph_begin_kernel and wipe B / n_act
-    CUDA_OK(cudaMemset(s->ctrl, 0, sizeof(PhaseCtrl)));
+    CUDA_OK(cudaMemset(s->ctrl, 0, kMaxPipes * sizeof(PhaseCtrl)));
     CUDA_OK(cudaStreamSynchronize(0));
-    CUDA_OK(cudaMalloc(&s->d_io, sizeof(SolveIO)));
-    CUDA_OK(cudaMallocHost(&s->h_ctrl, sizeof(PhaseCtrl)));
-  }
-  const long cap = (B + kPhaseThreads - 1) / kPhaseThreads * kPhaseThreads;
-  if (cap > s->cap) {
-    for (int i = 0; i < 2; ++i) {
-      if (s->act[i]) cudaFree(s->act[i]);
-      s->act[i] = nullptr;
+    CUDA_OK(cudaMalloc(&s->d_io, kMaxPipes * sizeof(SolveIO)));
+    CUDA_OK(cudaMallocHost(&s->h_ctrl, kMaxPipes * sizeof(PhaseCtrl)));
+    memset(s->h_ctrl, 0, kMaxPipes * sizeof(PhaseCtrl));
+    CUDA_OK(cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming));
+    for (int j = 0; j < kMaxPipes; ++j) {
+      s->pipe[j].ctrl = s->ctrl + j; s->pipe[j].d_io = s->d_io + j; s->pipe[j].h_ctrl = s->h_ctrl + j;
     }
-    if (s->retry) cudaFree(s->retry);
-    if (s->slow) cudaFree(s->slow);
-    s->retry = s->slow = nullptr;
-    s->cap = 0;
-    CUDA_OK(cudaMalloc(&s->act[0], cap * sizeof(int)));
-    CUDA_OK(cudaMalloc(&s->act[1], cap * sizeof(int)));
-    CUDA_OK(cudaMalloc(&s->retry, cap * sizeof(int)));
-    CUDA_OK(cudaMalloc(&s->slow, cap * sizeof(int)));
-    s->cap = cap;
-    if (s->exec) { cudaGraphExecDestroy(s->exec); s->exec = nullptr; }
-    if (s->graph) { cudaGraphDestroy(s->graph); s->graph = nullptr; }
   }
-  // thread-layout slab sized for the capacity (stride = cap)
-  const size_t need = (size_t)s->cap * h->L.total;
+  for (int j = 1; j < K; ++j) {
+    if (!s->pipe[j].stream) {
+      CUDA_OK(cudaStreamCreateWithFlags(&s->pipe[j].stream, cudaStreamNonBlocking));
+      CUDA_OK(cudaEventCreateWithFlags(&s->pipe[j].done, cudaEventDisableTiming));
+    }
+  }
+  const long share = (B + K - 1) / K;
+  const long cap = (share + kPhaseThreads - 1) / kPhaseThreads * kPhaseThreads;
+  bool relayout = false;
+  if (cap > s->cap || K != s->npipes) {
+    // keep the per-pipe capacity monotone so that alternating batch sizes do not reallocate every call
+    const long ncap = cap > s->cap ? cap : s->cap;
+    if ((long)K * ncap > (long)s->npipes * s->cap || !s->lists) {
+      if (s->lists) cudaFree(s->lists);
+      s->lists = nullptr;
+      s->cap = 0; s->npipes = 0;
+      CUDA_OK(cudaMalloc(&s->lists, (size_t)4 * K * ncap * sizeof(int)));
+    }
+    s->cap = ncap;
+    s->npipes = K;
+    relayout = true;
+  }
+  // workspace slabs sized for all pipes (pipe j owns the slots [j * cap, (j + 1) * cap))
+  const size_t need = (size_t)s->npipes * s->cap * h->L.total;
   if (need > h->slab_doubles) {
     if (h->slab) cudaFree(h->slab);
     h->slab = nullptr;
     h->slab_doubles = 0;
     CUDA_OK(cudaMalloc(&h->slab, need * sizeof(double)));
     h->slab_doubles = need;
+    relayout = true;
   }
   if (need > s->slab2_doubles) {
     if (s->slab2) cudaFree(s->slab2);
@@ -102,25 +156,34 @@ static int phase_ensure(mpcv_handle* h, long B) {
     s->slab2_doubles = 0;
     CUDA_OK(cudaMalloc(&s->slab2, need * sizeof(double)));
     s->slab2_doubles = need;
-    if (s->exec) { cudaGraphExecDestroy(s->exec); s->exec = nullptr; }
-    if (s->graph) { cudaGraphDestroy(s->graph); s->graph = nullptr; }
+    relayout = true;
   }
-  h->slab_stride = s->cap;
-  if (s->exec && (s->graph_slab != h->slab || s->graph_stride != h->slab_stride)) {
-    cudaGraphExecDestroy(s->exec); s->exec = nullptr;
-    cudaGraphDestroy(s->graph); s->graph = nullptr;
+  h->slab_stride = (long)s->npipes * s->cap;
+  if (s->graph_slab != h->slab) relayout = true;
+  if (relayout) {
+    phase_drop_graphs(s);
+    for (int j = 0; j < s->npipes; ++j) {
+      PhasePipe& q = s->pipe[j];
+      int* base = s->lists + (size_t)4 * j * s->cap;
+      q.act[0] = base; q.act[1] = base + s->cap; q.retry = base + 2 * s->cap; q.slow = base + 3 * s->cap;
+      q.slab[0] = h->slab + (size_t)j * s->cap * h->L.total;
+      q.slab[1] = s->slab2 + (size_t)j * s->cap * h->L.total;
+    }
+    s->graph_slab = h->slab;
+    s->graph_stride = h->slab_stride;
   }
   return 0;
 }
 
 template <class Model>
-static PhaseArgs phase_args(const mpcv_handle* h) {
+static PhaseArgs phase_args(const mpcv_handle* h, int j) {
   const mpcv_phase_state* s = h->phase;
+  const PhasePipe& q = s->pipe[j];
   PhaseArgs a;
-  a.P = h->P; a.L = h->L; a.slab[0] = h->slab; a.slab[1] = s->slab2;
-  a.act[0] = s->act[0]; a.act[1] = s->act[1];
-  a.retry = s->retry; a.slow = s->slow;
-  a.ctrl = s->ctrl; a.io = s->d_io; a.cap = s->cap;
+  a.P = h->P; a.L = h->L; a.slab[0] = q.slab[0]; a.slab[1] = q.slab[1];
+  a.act[0] = q.act[0]; a.act[1] = q.act[1];
+  a.retry = q.retry; a.slow = q.slow;
+  a.ctrl = q.ctrl; a.io = q.d_io; a.cap = s->cap;
   return a;
 }
 
@@ -162,9 +225,9 @@ static int add_kernel(cudaGraph_t g, cudaGraphNode_t* node, cudaGraphNode_t* dep
 }
 
 template <class Model>
-static int phase_build_graph(mpcv_handle* h) {
-  mpcv_phase_state* s = h->phase;
-  PhaseArgs a = phase_args<Model>(h);
+static int phase_build_graph(mpcv_handle* h, int j) {
+  PhasePipe* s = &h->phase->pipe[j];
+  PhaseArgs a = phase_args<Model>(h, j);
   const PhaseGrids gr = phase_grids(h);
   const size_t smem = phase_smem(h);
   int hess0 = 0, hess1 = 1, use_handle = 1;
@@ -208,8 +271,6 @@ static int phase_build_graph(mpcv_handle* h) {
   CUDA_OK(cudaGraphInstantiate(&exec, g, 0));
   s->graph = g;
   s->exec = exec;
-  s->graph_slab = h->slab;
-  s->graph_stride = h->slab_stride;
   return 0;
 }
 
@@ -217,8 +278,8 @@ static int phase_build_graph(mpcv_handle* h) {
 // kernels, the host reads the active count back every few sweeps
 template <class Model>
 static int phase_host_loop(mpcv_handle* h, cudaStream_t st) {
-  mpcv_phase_state* s = h->phase;
-  const PhaseArgs a = phase_args<Model>(h);
+  PhasePipe* s = &h->phase->pipe[0];
+  const PhaseArgs a = phase_args<Model>(h, 0);
   const PhaseGrids gr = phase_grids(h);
   const size_t smem = phase_smem(h);
   ph_init_kernel<Model><<<gr.prob, kPhaseThreads, smem, st>>>(a);
@@ -254,15 +315,33 @@ static int phase_host_loop(mpcv_handle* h, cudaStream_t st) {
   return 0;
 }
 
+// the share of the call's I/O that pipe j works on: problems [b0, b0 + nb)
+static SolveIO phase_sub_io(const mpcv_handle* h, const SolveIO& io, long b0) {
+  SolveIO q = io;
+  const long n = h->n_var, np = h->n_p, ng = h->n_g;
+  if (io.x0) q.x0 = io.x0 + b0 * n;
+  if (io.p) q.p = io.p + b0 * np;
+  if (io.x) q.x = io.x + b0 * n;
+  if (io.f) q.f = io.f + b0;
+  if (io.g) q.g = io.g + b0 * ng;
+  if (io.lam_g) q.lam_g = io.lam_g + b0 * ng;
+  if (io.lam_x) q.lam_x = io.lam_x + b0 * n;
+  if (io.status) q.status = io.status + b0;
+  if (io.iters) q.iters = io.iters + b0;
+  if (io.ns) q.ns = io.ns + b0;
+  return q;
+}
+
 template <class Model>
 static int launch_solve_phased(mpcv_handle* h, const SolveIO& io, long B, cudaStream_t st) {
   if (B <= 0) return 0;
   if (B > 0x7fffffffL) return mpcv_set_error(-EINVAL, "batch too large");
-  if (int rc = phase_ensure(h, B)) return rc;
+  const int K = phase_pipes_for(B);
+  if (int rc = phase_ensure(h, B, K)) return rc;
   mpcv_phase_state* s = h->phase;
   const size_t smem = phase_smem(h);
   if (smem > h->max_smem_optin) return mpcv_set_error(-ENOMEM, "bounds table exceeds shared memory; use MPCV_LAYOUT_WARP");
-  if (!s->exec && !s->graph_failed) {
+  if (!s->pipe[0].exec && !s->graph_failed) {
     if (phase_set_smem(ph_init_kernel<Model>, smem) || phase_set_smem(ph_der0_kernel<Model>, smem) ||
         phase_set_smem(ph_init2_kernel<Model>, smem) || phase_set_smem(ph_pre_kernel<Model>, smem) ||
         phase_set_smem(ph_factor_kernel<Model>, smem) || phase_set_smem(ph_post_kernel<Model>, smem) ||
@@ -272,24 +351,46 @@ static int launch_solve_phased(mpcv_handle* h, const SolveIO& io, long B, cudaSt
         phase_set_smem(ph_der_kernel<Model>, smem))
       return -EIO;
   }
-  ph_begin_kernel<<<1, 1, 0, st>>>(s->ctrl, s->d_io, io, (int)B);
-  h->launches++;
   const char* env = getenv("MPCV_PHASE_HOSTLOOP");
   const bool want_graph = !(env && env[0] == '1') && !s->graph_failed;
-  if (want_graph && !s->exec) {
-    if (phase_build_graph<Model>(h) != 0) {
-      // keep going with the host-driven loop; remember why
-      s->graph_failed = true;
-      cudaGetLastError();
-      if (s->exec) { cudaGraphExecDestroy(s->exec); s->exec = nullptr; }
+  if (want_graph) {
+    for (int j = 0; j < K && !s->graph_failed; ++j) {
+      if (s->pipe[j].exec) continue;
+      if (phase_build_graph<Model>(h, j) != 0) {
+        // keep going with the host-driven loop; remember why
+        s->graph_failed = true;
+        cudaGetLastError();
+        phase_drop_graphs(s);
+      }
     }
   }
-  if (want_graph && s->exec) {
-    CUDA_OK(cudaGraphLaunch(s->exec, st));
-    h->launches += 5;    // init chain + tail; the sweeps are counted from the device (mpcv_phase_sweeps)
+  if (want_graph && !s->graph_failed) {
+    // contiguous shares (multiples of 32 problems, so each share starts on a slab block); pipe 0 runs on the
+    // caller's stream, the others fork from it and join it again
+    const long share = ((B + K - 1) / K + 31) / 32 * 32;
+    if (K > 1) CUDA_OK(cudaEventRecord(s->fork, st));
+    for (int j = 0; j < K; ++j) {
+      const long b0 = j * share, nb = (b0 + share <= B) ? share : B - b0;
+      if (nb <= 0) break;
+      PhasePipe& q = s->pipe[j];
+      const cudaStream_t qs = j == 0 ? st : q.stream;
+      if (j > 0) CUDA_OK(cudaStreamWaitEvent(qs, s->fork, 0));
+      ph_begin_kernel<<<1, 1, 0, qs>>>(q.ctrl, q.d_io, phase_sub_io(h, io, b0), (int)nb);
+      CUDA_OK(cudaGraphLaunch(q.exec, qs));
+      h->launches += 6;    // begin + init chain + tail; the sweeps are counted from the device (mpcv_phase_sweeps)
+      if (j > 0) {
+        CUDA_OK(cudaEventRecord(q.done, qs));
+        CUDA_OK(cudaStreamWaitEvent(st, q.done, 0));
+      }
+    }
     h->phase_graph_launches++;
     return 0;
   }
+  // host-driven loop: one pipe over the whole batch (phase_pipes_for returns 1 when the environment asks for it;
+  // after a graph failure re-lay the lists out for one pipe)
+  if (K != 1) { if (int rc = phase_ensure(h, B, 1)) return rc; }
+  ph_begin_kernel<<<1, 1, 0, st>>>(s->pipe[0].ctrl, s->pipe[0].d_io, io, (int)B);
+  h->launches++;
   return phase_host_loop<Model>(h, st);
 }
 
@@ -297,7 +398,7 @@ static int launch_solve_phased(mpcv_handle* h, const SolveIO& io, long B, cudaSt
 template <class Model>
 static int launch_loop_phased(mpcv_handle* h, const LoopIO& io, long B, cudaStream_t st) {
   if (B <= 0) return 0;
-  if (int rc = phase_ensure(h, B)) return rc;
+  if (int rc = phase_ensure(h, B, phase_pipes_for(B))) return rc;
   mpcv_phase_state* s = h->phase;
   if (B > s->lb_cap) {
     loop_free(s);
@@ -339,10 +440,17 @@ static int launch_loop_phased(mpcv_handle* h, const LoopIO& io, long B, cudaStre
 
 static int phase_sweeps(mpcv_handle* h, cudaStream_t st, int* sweeps, int* cumulative) {
   if (!h->phase || !h->phase->ctrl) { *sweeps = 0; *cumulative = 0; return 0; }
-  CUDA_OK(cudaMemcpyAsync(h->phase->h_ctrl, h->phase->ctrl, sizeof(PhaseCtrl), cudaMemcpyDeviceToHost, st));
+  // summed over the pipes: every sweep of every pipe is 12 kernel launches
+  mpcv_phase_state* s = h->phase;
+  CUDA_OK(cudaMemcpyAsync(s->h_ctrl, s->ctrl, kMaxPipes * sizeof(PhaseCtrl), cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
-  *sweeps = h->phase->h_ctrl->sweeps_total;
-  *cumulative = h->phase->h_ctrl->sweeps_cum;
+  int tot = 0, cum = 0;
+  for (int j = 0; j < kMaxPipes; ++j) {
+    if (j < s->npipes) tot += s->h_ctrl[j].sweeps_total;
+    cum += s->h_ctrl[j].sweeps_cum;
+  }
+  *sweeps = tot;
+  *cumulative = cum;
   return 0;
 }
 

@@ -152,6 +152,32 @@ def test_unicycle_ms_warp_layout_equals_thread_layout(mv):
     assert np.abs(out[0][0]["x"] - out[1][0]["x"]).max() <= 1e-7
 
 
+def test_phase_pipes_split_the_batch_without_changing_results(mv, monkeypatch):
+    """Several pipes (independent pipeline instances over contiguous shares of the batch, each on its own stream)
+    against one pipe: every problem is solved by the same phase functions, only the hand-off to the tail kernel
+    (a function of the share's active count) can move an iteration between lane widths."""
+    x0s, p = common.unicycle_batch(5003, seed=23)          # ragged: not a multiple of 32 x pipes
+    monkeypatch.setenv("MPCV_PHASE_PIPE_MIN", "512")
+    out = []
+    for pipes in ("1", "3", "8"):
+        monkeypatch.setenv("MPCV_PHASE_PIPES", pipes)
+        solver = _solver(mv, problems.unicycle_multiple_shooting(), layout=S.LAYOUT_PHASED)
+        sp = solver.spec
+        lbx, ubx = problems.unicycle_bounds(sp, x_box=20.0)
+        sol = solver(x0=problems.cold_start(sp, x0s), lbx=lbx, ubx=ubx, p=p)
+        st = solver.stats()
+        assert st["success"]
+        again = solver(x0=problems.cold_start(sp, x0s), lbx=lbx, ubx=ubx, p=p)      # graph re-launch on every pipe
+        assert np.array_equal(again["x"], sol["x"]) and np.array_equal(again["f"], sol["f"])
+        out.append((sol, st["iter_count"]))
+    for sol, iters in out[1:]:
+        same = iters == out[0][1]
+        assert np.mean(same) >= 0.99
+        assert np.abs(sol["x"][same] - out[0][0]["x"][same]).max() <= 1e-9
+        assert np.abs(sol["x"] - out[0][0]["x"]).max() <= 1e-5
+        assert np.abs(sol["f"] - out[0][0]["f"]).max() <= 1e-6 * (1 + np.abs(out[0][0]["f"]).max())
+
+
 @pytest.mark.parametrize("hostloop", [False, True])
 def test_phased_layout_equals_thread_layout(mv, hostloop, monkeypatch):
     """The phase-kernel pipeline (one CUDA graph with a conditional WHILE node, or the host-driven
