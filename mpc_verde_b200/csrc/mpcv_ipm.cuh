@@ -75,7 +75,13 @@ struct Grp {
 // base pointer — no index arithmetic per access.
 struct WsStrided {
   double* base;
-  MPCV_HD double& operator[](int i) const { return base[(long)i * 32]; }
+  MPCV_HD double& operator[](int i) const {
+    double* p = base + (long)i * 32;
+#if defined(__CUDA_ARCH__)
+    __builtin_assume(__isGlobal(p));   // plain ld.global / st.global instead of generic accesses
+#endif
+    return *p;
+  }
   MPCV_HD static WsStrided of(double* slab, int total, long b) {
     double* p = slab + (b >> 5) * ((long)total * 32) + (b & 31);
 #if defined(__CUDA_ARCH__)
@@ -121,30 +127,37 @@ MPCV_HD Layout make_layout(int N) {
   L.N = N;
   L.n = SINGLE ? NU * N : NZ * N + NX;
   L.m = SINGLE ? 0 : NX * (N + 1);
+  // Region order: regions are grouped by the phases that read them, so that the part of a problem's workspace a
+  // lane-group kernel walks is one contiguous range of slab rows:
+  //   pre    [ab .. st]   (ab grad c lam zl zu qs w st; writes sig rb st)
+  //   accept [lam .. par) (lam zl zu qs w st d lamp ct + the x0 rows of par; writes w zl zu lam st)
+  // hw, ric, pp (Riccati kernels only) come last; ph_repack_kernel relies on ric, pp being the last two.
   int o = 0;
-  L.w = o; o += L.n;
-  L.zl = o; o += L.n;
-  L.zu = o; o += L.n;
-  L.d = o; o += L.n;
-  L.grad = o; o += L.n;
-  L.lam = o; o += NX * (N + 1);
+  L.lamp = L.c = L.ct = L.ric = L.pp = L.xs = L.hred = L.gam = L.tmp = 0;
   L.ab = o; o += N * (NX * NX + NX * NU);
-  L.hw = o; o += N * (NZ * (NZ + 1) / 2);
-  L.par = o; o += NX + Model::NPG + N * Model::NPS + 2;   // +2: alignment slack for bulk-staged stage params
+  L.grad = o; o += L.n;
   L.sig = o; o += L.n;
   L.rb = o; o += L.n;
+  if (!SINGLE) { L.c = o; o += L.m; }
+  L.lam = o; o += NX * (N + 1);
+  L.zl = o; o += L.n;
+  L.zu = o; o += L.n;
   L.qs = o; o += N;
+  L.w = o; o += L.n;
   L.st = o; o += kStateSlots;
-  L.lamp = L.c = L.ct = L.ric = L.pp = L.xs = L.hred = L.gam = L.tmp = 0;
+  L.d = o; o += L.n;
+  if (!SINGLE) {
+    L.lamp = o; o += L.m;
+    L.ct = o; o += L.m;
+  }
+  L.par = o; o += NX + Model::NPG + N * Model::NPS + 2;   // +2: alignment slack for bulk-staged stage params
+  L.hw = o; o += N * (NZ * (NZ + 1) / 2);
   if (SINGLE) {
     L.xs = o; o += NX * (N + 1);
     L.hred = o; o += (NU * N) * (NU * N + 1) / 2;
     L.gam = o; o += NX * NU * N;
     L.tmp = o; o += NZ * NU * N;
   } else {
-    L.lamp = o; o += L.m;
-    L.c = o; o += L.m;
-    L.ct = o; o += L.m;
     L.ric = o; o += N * (NU * NX + NU + NU * (NU + 1) / 2);
     L.pp = o; o += (N + 1) * (NX * (NX + 1) / 2 + NX);
   }
@@ -455,6 +468,21 @@ struct Ipm {
     g.sync();
   }
 
+  // Barrier log-sum  sum_i log(s_i)  accumulated as log of partial products: eight slacks per log() call.
+  // A slack lies between ~1e-11 (active bound at the final mu) and the width of the box, so a product of
+  // eight stays far inside the double range; the sum differs from the term-by-term one by a few ulp, far
+  // below the 10 eps |phi| slack of the filter's comparisons.  FP64 log is ~50 instructions: this is a
+  // quarter of the instructions of the line-search kernels.
+  struct LogSum {
+    double lg = 0.0, prod = 1.0;
+    int cnt = 0;
+    MPCV_D void add(double s) {
+      prod *= s;
+      if (++cnt == 8) { lg += log(prod); prod = 1.0; cnt = 0; }
+    }
+    MPCV_D double value() const { return cnt ? lg + log(prod) : lg; }
+  };
+
   // ---- objective / constraint violation / barrier at  w + alpha * (vector at doff) -------------
   // returns scaled f; theta = ||c||_1; barrier log terms; optionally stores the residuals in ct
   MPCV_DN void eval_trial(double alpha, int doff, bool store_ct, double* f_out, double* theta_out,
@@ -498,14 +526,16 @@ struct Ipm {
         }
       }
     }
+    LogSum ls;
     for (int i = g.lane; i < L.n; i += LANES) {
       const Bnd b = bnd(i);
       if (b.hasl || b.hasu) {
         const double v = ws[L.w + i] + alpha * ws[doff + i];
-        if (b.hasl) { const double s = v - b.lo; if (!(s > 0.0)) bad = true; logpart += log(s); }
-        if (b.hasu) { const double s = b.hi - v; if (!(s > 0.0)) bad = true; logpart += log(s); }
+        if (b.hasl) { const double s = v - b.lo; if (!(s > 0.0)) bad = true; ls.add(s); }
+        if (b.hasu) { const double s = b.hi - v; if (!(s > 0.0)) bad = true; ls.add(s); }
       }
     }
+    logpart = ls.value();
     const double f = df * g.sum(fpart);
     const double th = g.sum(thpart);
     double lg = g.sum(logpart);
@@ -538,14 +568,16 @@ struct Ipm {
       thpart += fabs(r);
       ws[L.ct + i] = r;
     }
+    LogSum ls;
     lane_loop(L.n, [&](int i) { return V2{ws[L.w + i], ws[doff + i]}; }, [&](int i, const V2& q) {
       const Bnd b = bnd(i);
       if (b.hasl || b.hasu) {
         const double v = q.a + alpha * q.b;
-        if (b.hasl) { const double s = v - b.lo; if (!(s > 0.0)) bad = true; logpart += log(s); }
-        if (b.hasu) { const double s = b.hi - v; if (!(s > 0.0)) bad = true; logpart += log(s); }
+        if (b.hasl) { const double s = v - b.lo; if (!(s > 0.0)) bad = true; ls.add(s); }
+        if (b.hasu) { const double s = b.hi - v; if (!(s > 0.0)) bad = true; ls.add(s); }
       }
     });
+    logpart = ls.value();
     const double f = sum_stage_costs();
     const double lg = g.sum(logpart);
     lg_trial = lg;
@@ -1233,47 +1265,35 @@ struct Ipm {
   }
 
   // ---- step-length helpers ----------------------------------------------------------------------------
-  // dz = mu / s - z - (z / s) d  with one reciprocal per bound
-  MPCV_D double dz_l(int i, const Bnd& b) const {
-    const double inv = 1.0 / (ws[L.w + i] - b.lo), z = ws[L.zl + i];
-    return mu * inv - z - z * inv * ws[L.d + i];
-  }
-  MPCV_D double dz_u(int i, const Bnd& b) const {
-    const double inv = 1.0 / (b.hi - ws[L.w + i]), z = ws[L.zu + i];
-    return mu * inv - z + z * inv * ws[L.d + i];
-  }
   MPCV_D double ftb_primal() const {
     double a = 1.0;
     lane_loop(L.n, [&](int i) { return V2{ws[L.w + i], ws[L.d + i]}; }, [&](int i, const V2& v) {
       const Bnd b = bnd(i);
       const double di = v.b;
-      if (b.hasl && di < 0.0) a = fmin(a, -tau * (v.a - b.lo) / di);
-      if (b.hasu && di > 0.0) a = fmin(a, tau * (b.hi - v.a) / di);
+      // num / di < a  <=>  num compared with a * di: divide only when the bound can shorten the step
+      if (b.hasl && di < 0.0) { const double num = -tau * (v.a - b.lo); if (num > a * di) a = fmin(a, num / di); }
+      if (b.hasu && di > 0.0) { const double num = tau * (b.hi - v.a); if (num < a * di) a = fmin(a, num / di); }
     });
     return g.min(a);
   }
-  // fraction-to-the-boundary rule for the bound multipliers.  The dual steps are parked in the (dead by
-  // now) Sigma / barrier-gradient slots for the update that follows.
+  // fraction-to-the-boundary rule for the bound multipliers
   MPCV_D double ftb_dual() const {
     double a = 1.0;
     lane_loop(L.n, [&](int i) { return V4{ws[L.w + i], ws[L.d + i], ws[L.zl + i], ws[L.zu + i]}; },
               [&](int i, const V4& v) {
       const Bnd b = bnd(i);
-      // dz = mu / s - z - (z / s) d  with one reciprocal per bound
-      if (b.hasl) {
-        const double inv = 1.0 / (v.a - b.lo), z = v.c;
-        const double dz = mu * inv - z - z * inv * v.b;
-        ws[L.sig + i] = dz;
-        if (dz < 0.0) a = fmin(a, -tau * z / dz);
-      }
-      if (b.hasu) {
-        const double inv = 1.0 / (b.hi - v.a), z = v.d;
-        const double dz = mu * inv - z + z * inv * v.b;
-        ws[L.rb + i] = dz;
-        if (dz < 0.0) a = fmin(a, -tau * z / dz);
-      }
+      // divide only when the bound multiplier can shorten the step (see ftb_primal)
+      if (b.hasl) { const double dz = dz_of(v.a - b.lo, v.c, -v.b), num = -tau * v.c; if (dz < 0.0 && num > a * dz) a = fmin(a, num / dz); }
+      if (b.hasu) { const double dz = dz_of(b.hi - v.a, v.d, v.b), num = -tau * v.d; if (dz < 0.0 && num > a * dz) a = fmin(a, num / dz); }
     });
     return g.min(a);
+  }
+  // dz = mu / s - z + (z / s) ds  with one reciprocal per bound (ds = -d for a lower, +d for an upper bound).
+  // Evaluated twice per accepted step (step length, then update) rather than parked in the workspace: a
+  // reciprocal is cheaper than a store and a load per bound, and the update then reads nothing but w, d, z.
+  MPCV_D double dz_of(double slack, double z, double ds) const {
+    const double inv = 1.0 / slack;
+    return mu * inv - z + z * inv * ds;
   }
   // z reset into [mu / (kappa_Sigma s), kappa_Sigma mu / s], kappa_Sigma = 1e10 (a safeguard that almost
   // never binds: test on z*s, divide only when it does)
@@ -1429,16 +1449,17 @@ struct Ipm {
     double theta = 0.0, gBD = 0.0, lg = 0.0;
     lane_loop(L.m, [&](int i) { return V1{ws[L.c + i]}; }, [&](int, const V1& v) { theta += fabs(v.a); });
     const bool need_lg = !lg_valid;
+    LogSum ls;
     lane_loop(L.n, [&](int i) { return V3{ws[L.rb + i], ws[L.d + i], ws[L.w + i]}; }, [&](int i, const V3& v) {
       const Bnd b = bnd(i);
       if (!b.fixed) gBD += v.a * v.b;
       if (need_lg) {
-        if (b.hasl) lg += log(v.c - b.lo);
-        if (b.hasu) lg += log(b.hi - v.c);
+        if (b.hasl) ls.add(v.c - b.lo);
+        if (b.hasu) ls.add(b.hi - v.c);
       }
     });
     theta = g.sum(theta); gBD = g.sum(gBD);
-    lg = need_lg ? g.sum(lg) : lg_curr;
+    lg = need_lg ? g.sum(ls.value()) : lg_curr;
     ls_theta = theta;
     ls_gBD = gBD;
     ls_phi = f_curr - mu * lg;
@@ -1493,13 +1514,13 @@ struct Ipm {
       }
     }
     const double alpha_dual = ftb_dual();
-    lane_loop(L.n, [&](int i) { return V6{ws[L.w + i], ws[L.d + i], ws[L.zl + i], ws[L.zu + i], ws[L.sig + i], ws[L.rb + i]}; },
-              [&](int i, const V6& v) {
+    lane_loop(L.n, [&](int i) { return V4{ws[L.w + i], ws[L.d + i], ws[L.zl + i], ws[L.zu + i]}; },
+              [&](int i, const V4& v) {
       const Bnd b = bnd(i);
       const double wi = v.a + alpha * v.b;
       ws[L.w + i] = wi;
-      if (b.hasl) ws[L.zl + i] = clamp_z(v.c + alpha_dual * v.e, wi - b.lo);
-      if (b.hasu) ws[L.zu + i] = clamp_z(v.d + alpha_dual * v.f, b.hi - wi);
+      if (b.hasl) ws[L.zl + i] = clamp_z(v.c + alpha_dual * dz_of(v.a - b.lo, v.c, -v.b), wi - b.lo);
+      if (b.hasu) ws[L.zu + i] = clamp_z(v.d + alpha_dual * dz_of(b.hi - v.a, v.d, v.b), b.hi - wi);
     });
     if (!SINGLE)
       lane_loop(L.m, [&](int i) { return V2{ws[L.lam + i], ws[L.lamp + i]}; },
@@ -1640,14 +1661,16 @@ struct Ipm {
         ws[L.ct + i] = r + alpha_soc * ws[L.ct + i];
       }
     }
+    LogSum ls;
     for (int i = g.lane; i < L.n; i += LANES) {
       const Bnd b = bnd(i);
       if (b.hasl || b.hasu) {
         const double v = ws[L.w + i] + alpha_soc * ws[L.d + i];
-        if (b.hasl) { const double s = v - b.lo; if (!(s > 0.0)) bad = true; logpart += log(s); }
-        if (b.hasu) { const double s = b.hi - v; if (!(s > 0.0)) bad = true; logpart += log(s); }
+        if (b.hasl) { const double s = v - b.lo; if (!(s > 0.0)) bad = true; ls.add(s); }
+        if (b.hasu) { const double s = b.hi - v; if (!(s > 0.0)) bad = true; ls.add(s); }
       }
     }
+    logpart = ls.value();
     const double f = df * g.sum(fpart);
     const double lg = g.sum(logpart);
     lg_trial = lg;

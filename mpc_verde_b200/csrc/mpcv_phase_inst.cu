@@ -188,7 +188,6 @@ static PhaseArgs phase_args(const mpcv_handle* h, int j) {
 }
 
 static size_t phase_smem(const mpcv_handle* h) { return (size_t)h->L.n * sizeof(BndEntry); }
-
 // fixed grids: enough CTAs to fill the GPU once (never more than the work of a full batch needs)
 struct PhaseGrids { unsigned prob, stage, warp, group; };
 static PhaseGrids phase_grids(const mpcv_handle* h) {
