@@ -630,18 +630,63 @@ __global__ void __launch_bounds__(kWarpPhaseThreads, MPCV_GROUP_MINB) ph_accept_
   else ph_accept_run<Model, kGroupLanes>(a, slab, io, tab, out, n);
 }
 
+// ---- warp-per-problem kernels: the problem's workspace staged in shared memory ------------------------------
+// ph_slow_kernel and ph_tail_kernel run a long dependent chain per problem (trial evaluations, Riccati re-solves,
+// whole iterations) on a few warps: every access to the slab is an exposed HBM round trip.  They are register-
+// bound at two CTAs per SM, so shared memory is free: the warp copies its problem's workspace into a shared row
+// (cp.async, every element in flight at once), runs the unchanged phase body on the row, and writes back what
+// the sweeps read afterwards (slow) or nothing at all (tail: the problem is finished and exported from the row).
+// (generic addressing on purpose: with __builtin_assume(__isShared(p)) nvcc 12.9 miscompiles the 32-lane phase
+// bodies — the same source on generic pointers is bit-identical to the run on the slab)
+struct WsShared {
+  double* row;
+  __device__ __forceinline__ double& operator[](int i) const { return row[i]; }
+};
+__device__ __forceinline__ void ph_cp_async8(double* dst_smem, const double* src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void ph_cp_async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// shared rows of a CTA start after the bounds table
+__host__ __device__ inline size_t ph_rows_offset(const Layout& L) { return ((size_t)L.n * sizeof(BndEntry) + 15) & ~(size_t)15; }
+__device__ __forceinline__ double* ph_row_of_warp(const Layout& L, int warp) {
+  extern __shared__ __align__(16) unsigned char ph_smem[];
+  return reinterpret_cast<double*>(ph_smem + ph_rows_offset(L)) + (long)warp * L.total;
+}
+__device__ __forceinline__ void ph_stage_in(const Layout& L, const WsStrided& ws, double* row, int lane) {
+  for (int i = lane; i < L.total; i += 32) ph_cp_async8(row + i, &ws[i]);
+  ph_cp_async_wait();
+  __syncwarp();
+}
+
+// `staged` = 1: dynamic shared memory holds one workspace row per warp
 template <class Model>
-__global__ void __launch_bounds__(kWarpPhaseThreads) ph_slow_kernel(const __grid_constant__ PhaseArgs a) {
+__global__ void __launch_bounds__(kWarpPhaseThreads) ph_slow_kernel(const __grid_constant__ PhaseArgs a, int staged) {
   double* const slab = a.slab[ph_cur_after_repack(a.ctrl)];
   const int n = a.ctrl->n_slow;
   const int wpb = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if ((long)blockIdx.x * wpb >= n) return;
   const SolveIO io = *a.io;
   const BndEntry* tab = ph_bounds_table<Model>(a.P, a.L, io);
+  const Layout& L = a.L;
   for (long e = (long)blockIdx.x * wpb + warp; e < n; e += (long)gridDim.x * wpb) {
     const int b = a.slow[e];
-    Phase<Model, WsStrided, 32>::slow_body(a.P, a.L, WsStrided::of(slab, a.L.total, b), io, b, tab,
-                                           Grp<32>(lane), io.ns ? ph_globaltimer() : 0);
+    const WsStrided ws = WsStrided::of(slab, L.total, b);
+    const long long now = io.ns ? ph_globaltimer() : 0;
+    if (staged) {
+      double* const row = ph_row_of_warp(L, warp);
+      ph_stage_in(L, ws, row, lane);
+      const WsShared sw{row};
+      Phase<Model, WsShared, 32>::slow_body(a.P, L, sw, io, b, tab, Grp<32>(lane), now);
+      __syncwarp();
+      // what the sweeps read next: the iterate, its multipliers and the solve state (d, lam+, the trial residuals
+      // and the parked step in hw are dead: the derivative sweep and the next factorisation rewrite them)
+      auto put = [&](int off, int cnt) { for (int i = lane; i < cnt; i += 32) ws[off + i] = sw[off + i]; };
+      put(L.w, L.n); put(L.zl, L.n); put(L.zu, L.n); put(L.lam, L.m); put(L.st, kStateSlots);
+      __syncwarp();
+    } else {
+      Phase<Model, WsStrided, 32>::slow_body(a.P, L, ws, io, b, tab, Grp<32>(lane), now);
+    }
   }
 }
 
@@ -670,7 +715,7 @@ __global__ void __launch_bounds__(kPhaseThreads) ph_der_kernel(const __grid_cons
 #define MPCV_TAIL_MINB 1
 #endif
 template <class Model>
-__global__ void __launch_bounds__(kWarpPhaseThreads, MPCV_TAIL_MINB) ph_tail_kernel(const __grid_constant__ PhaseArgs a) {
+__global__ void __launch_bounds__(kWarpPhaseThreads, MPCV_TAIL_MINB) ph_tail_kernel(const __grid_constant__ PhaseArgs a, int staged) {
   double* const slab = a.slab[a.ctrl->cur];
   const int in = a.ctrl->sweep & 1;
   const int n = a.ctrl->n_act[in];
@@ -680,8 +725,17 @@ __global__ void __launch_bounds__(kWarpPhaseThreads, MPCV_TAIL_MINB) ph_tail_ker
   const BndEntry* tab = ph_bounds_table<Model>(a.P, a.L, io);
   for (long e = (long)blockIdx.x * wpb + warp; e < n; e += (long)gridDim.x * wpb) {
     const int b = a.act[in][e];
-    Phase<Model, WsStrided, 32>::tail_body(a.P, a.L, WsStrided::of(slab, a.L.total, b), io, b, tab, Grp<32>(lane),
-                                           io.ns ? ph_globaltimer() : 0);
+    const WsStrided ws = WsStrided::of(slab, a.L.total, b);
+    const long long now = io.ns ? ph_globaltimer() : 0;
+    if (staged) {
+      // the problem runs to completion and is exported from the row: nothing goes back to the slab
+      double* const row = ph_row_of_warp(a.L, warp);
+      ph_stage_in(a.L, ws, row, lane);
+      Phase<Model, WsShared, 32>::tail_body(a.P, a.L, WsShared{row}, io, b, tab, Grp<32>(lane), now);
+      __syncwarp();
+    } else {
+      Phase<Model, WsStrided, 32>::tail_body(a.P, a.L, ws, io, b, tab, Grp<32>(lane), now);
+    }
   }
 }
 

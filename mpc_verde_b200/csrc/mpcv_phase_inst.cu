@@ -188,6 +188,19 @@ static PhaseArgs phase_args(const mpcv_handle* h, int j) {
 }
 
 static size_t phase_smem(const mpcv_handle* h) { return (size_t)h->L.n * sizeof(BndEntry); }
+// warp-per-problem kernels (slow, tail): bounds table + one workspace row per warp, when it fits
+// (MPCV_WARP_STAGED=0 keeps them on the slab: A/B measurements)
+static size_t warp_staged_smem(const mpcv_handle* h) {
+  return ph_rows_offset(h->L) + (size_t)(kWarpPhaseThreads / 32) * h->L.total * sizeof(double);
+}
+// bit 0: ph_slow_kernel, bit 1: ph_tail_kernel
+static int warp_staged_mask(const mpcv_handle* h) {
+  int mask = 3;
+  if (const char* env = getenv("MPCV_WARP_STAGED")) mask = atoi(env) & 3;
+  return warp_staged_smem(h) <= h->max_smem_optin ? mask : 0;
+}
+static bool warp_staged(const mpcv_handle* h) { return warp_staged_mask(h) != 0; }
+static size_t warp_smem(const mpcv_handle* h) { return warp_staged(h) ? warp_staged_smem(h) : phase_smem(h); }
 // fixed grids: enough CTAs to fill the GPU once (never more than the work of a full batch needs)
 struct PhaseGrids { unsigned prob, stage, warp, group; };
 static PhaseGrids phase_grids(const mpcv_handle* h) {
@@ -250,6 +263,9 @@ static int phase_build_graph(mpcv_handle* h, int j) {
   CUDA_OK(cudaGraphAddNode(&n_while, g, &n_der1, 1, &cp));
   cudaGraph_t body = cp.conditional.phGraph_out[0];
   cudaGraphNode_t b_probe, b_pre, b_repack, b_relist, b_factor, b_retry, b_post, b_trial, b_accept, b_slow, b_der, b_flip;
+  int staged_slow = warp_staged_mask(h) & 1, staged_tail = (warp_staged_mask(h) >> 1) & 1;
+  void* a_slow[] = {&a, &staged_slow};
+  void* a_tail[] = {&a, &staged_tail};
   void* a_flip[] = {&s->ctrl, &handle, &use_handle};
   if (int rc = add_kernel(body, &b_pre, nullptr, (void*)ph_pre_kernel<Model>, gr.group, kWarpPhaseThreads, smem, a_init)) return rc;
   if (int rc = add_kernel(body, &b_repack, &b_pre, (void*)ph_repack_kernel<Model>, gr.prob, kPhaseThreads, 0, a_init)) return rc;
@@ -260,12 +276,12 @@ static int phase_build_graph(mpcv_handle* h, int j) {
   if (int rc = add_kernel(body, &b_post, &b_retry, (void*)ph_post_kernel<Model>, gr.group, kWarpPhaseThreads, smem, a_init)) return rc;
   if (int rc = add_kernel(body, &b_trial, &b_post, (void*)ph_trial_kernel<Model>, gr.stage, kPhaseThreads, smem, a_init)) return rc;
   if (int rc = add_kernel(body, &b_accept, &b_trial, (void*)ph_accept_kernel<Model>, gr.group, kWarpPhaseThreads, smem, a_init)) return rc;
-  if (int rc = add_kernel(body, &b_slow, &b_accept, (void*)ph_slow_kernel<Model>, gr.warp, kWarpPhaseThreads, smem, a_init)) return rc;
+  if (int rc = add_kernel(body, &b_slow, &b_accept, (void*)ph_slow_kernel<Model>, gr.warp, kWarpPhaseThreads, warp_smem(h), a_slow)) return rc;
   if (int rc = add_kernel(body, &b_der, &b_slow, (void*)ph_der_kernel<Model>, gr.stage, kPhaseThreads, smem, a_init)) return rc;
   if (int rc = add_kernel(body, &b_flip, &b_der, (void*)ph_flip_kernel, 1, 1, 0, a_flip)) return rc;
   // the stragglers finish in one persistent kernel after the loop
   cudaGraphNode_t n_tail;
-  if (int rc = add_kernel(g, &n_tail, &n_while, (void*)ph_tail_kernel<Model>, gr.warp, kWarpPhaseThreads, smem, a_init)) return rc;
+  if (int rc = add_kernel(g, &n_tail, &n_while, (void*)ph_tail_kernel<Model>, gr.warp, kWarpPhaseThreads, warp_smem(h), a_tail)) return rc;
   cudaGraphExec_t exec = nullptr;
   CUDA_OK(cudaGraphInstantiate(&exec, g, 0));
   s->graph = g;
@@ -299,7 +315,7 @@ static int phase_host_loop(mpcv_handle* h, cudaStream_t st) {
       ph_post_kernel<Model><<<gr.group, kWarpPhaseThreads, smem, st>>>(a);
       ph_trial_kernel<Model><<<gr.stage, kPhaseThreads, smem, st>>>(a);
       ph_accept_kernel<Model><<<gr.group, kWarpPhaseThreads, smem, st>>>(a);
-      ph_slow_kernel<Model><<<gr.warp, kWarpPhaseThreads, smem, st>>>(a);
+      ph_slow_kernel<Model><<<gr.warp, kWarpPhaseThreads, warp_smem(h), st>>>(a, warp_staged_mask(h) & 1);
       ph_der_kernel<Model><<<gr.stage, kPhaseThreads, smem, st>>>(a);
       ph_flip_kernel<<<1, 1, 0, st>>>(s->ctrl, none, 0);
       h->launches += 12;
@@ -308,7 +324,7 @@ static int phase_host_loop(mpcv_handle* h, cudaStream_t st) {
     CUDA_OK(cudaStreamSynchronize(st));
     if (s->h_ctrl->n_act[s->h_ctrl->sweep & 1] <= ph_tail_below(s->h_ctrl->B)) break;
   }
-  ph_tail_kernel<Model><<<gr.warp, kWarpPhaseThreads, smem, st>>>(a);
+  ph_tail_kernel<Model><<<gr.warp, kWarpPhaseThreads, warp_smem(h), st>>>(a, (warp_staged_mask(h) >> 1) & 1);
   h->launches++;
   CUDA_OK(cudaGetLastError());
   return 0;
@@ -345,8 +361,8 @@ static int launch_solve_phased(mpcv_handle* h, const SolveIO& io, long B, cudaSt
         phase_set_smem(ph_init2_kernel<Model>, smem) || phase_set_smem(ph_pre_kernel<Model>, smem) ||
         phase_set_smem(ph_factor_kernel<Model>, smem) || phase_set_smem(ph_post_kernel<Model>, smem) ||
         phase_set_smem(ph_trial_kernel<Model>, smem) || phase_set_smem(ph_accept_kernel<Model>, smem) ||
-        phase_set_smem(ph_retry_kernel<Model>, smem) || phase_set_smem(ph_probe_kernel<Model>, smem) || phase_set_smem(ph_slow_kernel<Model>, smem) ||
-        phase_set_smem(ph_tail_kernel<Model>, smem) ||
+        phase_set_smem(ph_retry_kernel<Model>, smem) || phase_set_smem(ph_probe_kernel<Model>, smem) || phase_set_smem(ph_slow_kernel<Model>, warp_smem(h)) ||
+        phase_set_smem(ph_tail_kernel<Model>, warp_smem(h)) ||
         phase_set_smem(ph_der_kernel<Model>, smem))
       return -EIO;
   }

@@ -3,6 +3,8 @@
 // C++ with one lane per problem so that the interior-point logic can be unit-tested against
 // the oracle in a container without a GPU.  Nothing in mpc_verde_b200/ loads this library;
 // the shipped library (libmpcv.so) contains CUDA kernels only and errors out without a GPU.
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -58,14 +60,17 @@ static int hs_solve_phased_t(const mpcv_spec* s, const SolveIO& io, long B, int*
     }
     for (int e = 0; e < n_act[out]; ++e)                                    // factor
       if (!Ph::factor_body(P, L, ws(act[out][e]), io, tab.data())) retry.push_back(act[out][e]);
+    int won[Ph::kProbe + 1] = {};
     for (int b : retry) {                                                    // probe (kProbe attempts, no stores)
       bool found = false;
       double dsel = 0.0;
-      for (int a = 0; a < Ph::kProbe && !found; ++a) {
+      int a = 0;
+      for (; a < Ph::kProbe && !found; ++a) {
         double dw;
         found = Ph::probe_body(P, L, ws(b), io, tab.data(), a, &dw);
         dsel = dw;
       }
+      won[found ? a - 1 : Ph::kProbe]++;
       if (found) Ph::apply_body(P, L, ws(b), io, tab.data(), dsel);     // the winning lane completes the step
       else ws(b)[L.st + kSlotDwHint] = -dsel;
     }
@@ -85,6 +90,12 @@ static int hs_solve_phased_t(const mpcv_spec* s, const SolveIO& io, long B, int*
         const int b = act[out][e];
         if (Ph::running(L, ws(b))) Ph::der_body(P, L, ws(b), io, k, true, tab.data());
       }
+    if (getenv("HS_STATS")) {
+      // schedule statistics the kernel shapes were chosen from: active, wrong inertia (winning probe attempt), slow path
+      fprintf(stderr, "sweep %2d active %6d retry %6zu won", sweep, n_act[out], retry.size());
+      for (int a = 0; a <= Ph::kProbe; ++a) fprintf(stderr, " %d", won[a]);
+      fprintf(stderr, " slow %zu\n", slow.size());
+    }
     n_act[in] = 0;
     ++sweep;
   }
