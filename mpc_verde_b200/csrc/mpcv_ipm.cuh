@@ -1265,28 +1265,34 @@ struct Ipm {
   }
 
   // ---- step-length helpers ----------------------------------------------------------------------------
+  // Fraction-to-the-boundary rules.  alpha = min(1, min_i num_i / den_i) over the bounds the step moves towards
+  // (num_i, den_i < 0).  The minimum is tracked as a (num, den) pair compared by cross-multiplication,
+  // num_i den_best < num_best den_i, and divided once per lane at the end: no FP64 division (and no divergent
+  // slow path of it) inside the loop; the value is the quotient of the minimising bound, as before.
+  struct Ratio {
+    double num = -1.0, den = -1.0;     // 1
+    MPCV_D void take(double n, double d) { if (d < 0.0 && n * den < num * d) { num = n; den = d; } }
+    MPCV_D double value() const { return num / den; }
+  };
   MPCV_D double ftb_primal() const {
-    double a = 1.0;
+    Ratio r;
     lane_loop(L.n, [&](int i) { return V2{ws[L.w + i], ws[L.d + i]}; }, [&](int i, const V2& v) {
       const Bnd b = bnd(i);
-      const double di = v.b;
-      // num / di < a  <=>  num compared with a * di: divide only when the bound can shorten the step
-      if (b.hasl && di < 0.0) { const double num = -tau * (v.a - b.lo); if (num > a * di) a = fmin(a, num / di); }
-      if (b.hasu && di > 0.0) { const double num = tau * (b.hi - v.a); if (num < a * di) a = fmin(a, num / di); }
+      if (b.hasl) r.take(-tau * (v.a - b.lo), v.b);
+      if (b.hasu) r.take(-tau * (b.hi - v.a), -v.b);
     });
-    return g.min(a);
+    return g.min(r.value());
   }
   // fraction-to-the-boundary rule for the bound multipliers
   MPCV_D double ftb_dual() const {
-    double a = 1.0;
+    Ratio r;
     lane_loop(L.n, [&](int i) { return V4{ws[L.w + i], ws[L.d + i], ws[L.zl + i], ws[L.zu + i]}; },
               [&](int i, const V4& v) {
       const Bnd b = bnd(i);
-      // divide only when the bound multiplier can shorten the step (see ftb_primal)
-      if (b.hasl) { const double dz = dz_of(v.a - b.lo, v.c, -v.b), num = -tau * v.c; if (dz < 0.0 && num > a * dz) a = fmin(a, num / dz); }
-      if (b.hasu) { const double dz = dz_of(b.hi - v.a, v.d, v.b), num = -tau * v.d; if (dz < 0.0 && num > a * dz) a = fmin(a, num / dz); }
+      if (b.hasl) r.take(-tau * v.c, dz_of(v.a - b.lo, v.c, -v.b));
+      if (b.hasu) r.take(-tau * v.d, dz_of(b.hi - v.a, v.d, v.b));
     });
-    return g.min(a);
+    return g.min(r.value());
   }
   // dz = mu / s - z + (z / s) ds  with one reciprocal per bound (ds = -d for a lower, +d for an upper bound).
   // Evaluated twice per accepted step (step length, then update) rather than parked in the workspace: a

@@ -322,7 +322,7 @@ static int phase_host_loop(mpcv_handle* h, cudaStream_t st) {
     }
     CUDA_OK(cudaMemcpyAsync(s->h_ctrl, s->ctrl, sizeof(PhaseCtrl), cudaMemcpyDeviceToHost, st));
     CUDA_OK(cudaStreamSynchronize(st));
-    if (s->h_ctrl->n_act[s->h_ctrl->sweep & 1] <= ph_tail_below(s->h_ctrl->B)) break;
+    if (s->h_ctrl->n_act[s->h_ctrl->sweep & 1] <= s->h_ctrl->tail_below) break;
   }
   ph_tail_kernel<Model><<<gr.warp, kWarpPhaseThreads, warp_smem(h), st>>>(a, (warp_staged_mask(h) >> 1) & 1);
   h->launches++;
@@ -390,7 +390,7 @@ static int launch_solve_phased(mpcv_handle* h, const SolveIO& io, long B, cudaSt
       PhasePipe& q = s->pipe[j];
       const cudaStream_t qs = j == 0 ? st : q.stream;
       if (j > 0) CUDA_OK(cudaStreamWaitEvent(qs, s->fork, 0));
-      ph_begin_kernel<<<1, 1, 0, qs>>>(q.ctrl, q.d_io, phase_sub_io(h, io, b0), (int)nb);
+      ph_begin_kernel<<<1, 1, 0, qs>>>(q.ctrl, q.d_io, phase_sub_io(h, io, b0), (int)nb, ph_tail_below((int)nb));
       CUDA_OK(cudaGraphLaunch(q.exec, qs));
       h->launches += 6;    // begin + init chain + tail; the sweeps are counted from the device (mpcv_phase_sweeps)
       if (j > 0) {
@@ -404,7 +404,7 @@ static int launch_solve_phased(mpcv_handle* h, const SolveIO& io, long B, cudaSt
   // host-driven loop: one pipe over the whole batch (phase_pipes_for returns 1 when the environment asks for it;
   // after a graph failure re-lay the lists out for one pipe)
   if (K != 1) { if (int rc = phase_ensure(h, B, 1)) return rc; }
-  ph_begin_kernel<<<1, 1, 0, st>>>(s->pipe[0].ctrl, s->pipe[0].d_io, io, (int)B);
+  ph_begin_kernel<<<1, 1, 0, st>>>(s->pipe[0].ctrl, s->pipe[0].d_io, io, (int)B, ph_tail_below((int)B));
   h->launches++;
   return phase_host_loop<Model>(h, st);
 }
