@@ -143,6 +143,8 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="problems per GPU per step")
     ap.add_argument("--layout", type=int, default=S.LAYOUT_AUTO)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gather", default="inline", choices=["inline", "overlap"],
+                    help="N>1: NCCL gather of the results in stream order after each solve, or on a side stream under the next solve")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -180,14 +182,19 @@ def main():
         sol = solver(x0=w0, lbx=lb, ubx=ub, p=p, outputs=("x", "f"))
         return sol
 
-    # result gather + statistics over NCCL, on a side stream so that it runs underneath the next step's solve
-    # (no host synchronisation inside; the timed region ends only after the last gather has finished)
-    gstream = torch.cuda.Stream(device=dev) if world > 1 else None
+    # result gather + statistics over NCCL, no host synchronisation inside; the timed region ends only after the
+    # last gather has finished.  "inline": in stream order right after the solve (0.3-0.8 ms per step).  "overlap":
+    # on a side stream underneath the next step's solve — measured slower since the solve runs several pipes
+    # at once: the NCCL kernels of the two ranks wait for SM slots behind the other rank's sweeps (N=2: 33.0 ms
+    # per step against 17.4 ms at N=1).
+    gstream = torch.cuda.Stream(device=dev) if (world > 1 and args.gather == "overlap") else None
 
     def gather(sol):
         if world == 1:
             return None
         st, it = solver._last
+        if gstream is None:
+            return mdist.gather_rows_equal(sol["x"]), mdist.gather_rows_equal(sol["f"]), mdist.reduce_stats_device(st, it)
         done = torch.cuda.Event()
         done.record()
         with torch.cuda.stream(gstream):
@@ -322,7 +329,7 @@ def main():
                                "x,y in [-20,20], v in [-1,1], w in [-pi/4,pi/4]",
                    "batch_per_gpu": B, "global_batch": world * B, "seed": SEED, "l2": "flushed between steps (256 MB write)",
                    "layout": {0: "auto (phase kernels)", 1: "thread-per-problem", 2: "warp-per-problem", 3: "phase kernels"}[args.layout],
-                   "parallelism": "problem-index sharding x%d, NCCL all-gather of results + stats on a side stream" % world},
+                   "parallelism": "problem-index sharding x%d, NCCL all-gather of results + stats (%s)" % (world, args.gather)},
         "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "steps": e2e_steps},
         "gpu_launches": int(launches),
