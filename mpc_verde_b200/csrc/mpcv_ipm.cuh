@@ -1509,6 +1509,12 @@ struct Ipm {
   }
   // filter augmentation, dual step length and the update of (w, z, lam) for an accepted step
   MPCV_D void ls_accept_step(double alpha, double alpha_test, double phi_acc, const LsPow& pw) {
+    ls_filter_augment(alpha_test, phi_acc, pw);
+    ls_take_step(alpha);
+  }
+  // (the two halves are separate so that a lane-group kernel can bring its warp back together between the
+  // branchy scalar part and the loops over the variables, see ph_accept_kernel)
+  MPCV_D void ls_filter_augment(double alpha_test, double phi_acc, const LsPow& pw) {
     const double theta = ls_theta, phi = ls_phi;
     if (!ls_is_ftype(alpha_test, pw) || !ls_armijo(alpha_test, phi_acc)) {
       if (nfil < FILTER_MAX) {
@@ -1519,6 +1525,8 @@ struct Ipm {
         fil_phi[FILTER_MAX - 1] = phi - 1e-8 * theta; fil_th[FILTER_MAX - 1] = (1.0 - 1e-5) * theta;
       }
     }
+  }
+  MPCV_D void ls_take_step(double alpha) {
     const double alpha_dual = ftb_dual();
     lane_loop(L.n, [&](int i) { return V4{ws[L.w + i], ws[L.d + i], ws[L.zl + i], ws[L.zu + i]}; },
               [&](int i, const V4& v) {
@@ -1541,12 +1549,19 @@ struct Ipm {
   // Fast path of the phase pipeline: the full step (alpha = ls_alpha_max, stage part already evaluated by
   // trial_stage) is accepted by the filter — no backtracking, no second-order correction.  Returns false
   // without touching the iterate when the slow path (line_search(true)) has to take over.
+  struct LsFirst { LsPow pw; double phi_t; bool ok; };
+  MPCV_D LsFirst line_search_first_decide() {
+    LsFirst r;
+    r.pw = ls_pows();
+    double f_t, theta_t;
+    trial_reduce(ls_alpha_max, L.d, &f_t, &theta_t, &r.phi_t);
+    r.ok = ls_acceptable(ls_alpha_max, r.phi_t, theta_t, r.pw);
+    return r;
+  }
   MPCV_DN bool line_search_first() {
-    const LsPow pw = ls_pows();
-    double f_t, theta_t, phi_t;
-    trial_reduce(ls_alpha_max, L.d, &f_t, &theta_t, &phi_t);
-    if (!ls_acceptable(ls_alpha_max, phi_t, theta_t, pw)) return false;
-    ls_accept_step(ls_alpha_max, ls_alpha_max, phi_t, pw);
+    const LsFirst r = line_search_first_decide();
+    if (!r.ok) return false;
+    ls_accept_step(ls_alpha_max, ls_alpha_max, r.phi_t, r.pw);
     return true;
   }
 

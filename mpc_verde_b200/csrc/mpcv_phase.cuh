@@ -603,17 +603,38 @@ __global__ void __launch_bounds__(kPhaseThreads) ph_trial_kernel(const __grid_co
   }
 }
 
+// The decision (switching condition, Armijo / filter tests, filter augmentation) is branchy scalar code on which
+// the problems of a warp part ways; the step that follows is two loops over the variables.  Left to the compiler
+// the groups do not come back together before the loops (measured at sweep 9 of C2: the update ran twice per warp
+// with 12 of 32 lanes each), so the warp is synchronised explicitly between the two halves; the pass loop is
+// warp-uniform for that.
 template <class Model, int LANES>
 __device__ __forceinline__ void ph_accept_run(const PhaseArgs& a, double* slab, const SolveIO& io, const BndEntry* tab,
                                               int out, int n) {
+  using IpmT = Ipm<Model, false, LANES, WsStrided>;
   const int gpb = blockDim.x / LANES, grp = threadIdx.x / LANES;
   const Grp<LANES> g(threadIdx.x & 31);
-  for (long e = (long)blockIdx.x * gpb + grp; e < n; e += (long)gridDim.x * gpb) {
-    const int b = a.act[out][e];
+  for (long e0 = (long)blockIdx.x * gpb; e0 < n; e0 += (long)gridDim.x * gpb) {
+    const long e = e0 + grp;
+    bool act = e < n;
+    const int b = act ? a.act[out][e] : 0;
     const WsStrided ws = WsStrided::of(slab, a.L.total, b);
-    if (!Phase<Model, WsStrided>::running(a.L, ws)) continue;
-    const bool ok = Phase<Model, WsStrided, LANES>::accept_body(a.P, a.L, ws, io, tab, g);
-    if (!ok && g.lane == 0) a.slow[atomicAdd(&a.ctrl->n_slow, 1)] = b;
+    act = act && Phase<Model, WsStrided>::running(a.L, ws);
+    IpmT ipm(a.P, a.L, ws, g, io.lbx, io.ubx, tab);
+    typename IpmT::LsFirst r;
+    r.ok = false;
+    if (act) {
+      ipm.load_state();
+      r = ipm.line_search_first_decide();
+      if (r.ok) ipm.ls_filter_augment(ipm.ls_alpha_max, r.phi_t, r.pw);
+    }
+    __syncwarp();
+    if (act && r.ok) {
+      ipm.ls_take_step(ipm.ls_alpha_max);
+      ipm.save_state(kRunning);
+    } else if (act && g.lane == 0) {
+      a.slow[atomicAdd(&a.ctrl->n_slow, 1)] = b;
+    }
   }
 }
 
