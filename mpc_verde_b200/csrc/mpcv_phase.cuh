@@ -71,7 +71,7 @@ constexpr int kRepackSplit = MPCV_REPACK_SPLIT;
 #endif
 constexpr int kTailBelow = MPCV_TAIL_BELOW;    // at most this many active problems: leave the sweeps, finish in ph_tail_kernel
 #ifndef MPCV_WIDE_BELOW
-#define MPCV_WIDE_BELOW 16384   /* fewer active problems than this: latency-bound, use MPCV_WIDE_LANES lanes per problem */
+#define MPCV_WIDE_BELOW 8192   /* fewer active problems (per pipe) than this: latency-bound, use MPCV_WIDE_LANES lanes per problem; 4 pipes x 16,384: 16384: 16.6 ms, 8192: 16.1, 4096: 16.1 */
 #endif
 #ifndef MPCV_WIDE_LANES
 #define MPCV_WIDE_LANES 8   /* C4 (4,096 scenarios x 100 steps): 4 lanes 354 ms, 8 lanes 299 ms, 32 lanes 426 ms */
