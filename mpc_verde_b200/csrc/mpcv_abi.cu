@@ -315,30 +315,52 @@ int mpcv_solve_host(mpcv_handle* h, const double* x0, const double* lbx, const d
   char* hp = (char*)h->hpin;
   char* dp = (char*)h->dstage;
   cudaStream_t st = h->own_stream;
-  struct Xfer { const void* user; size_t off, bytes; };
-  const Xfer ins[] = {{x0, o_x0, x0 ? (size_t)B * n * 8 : 0}, {lbx, o_lb, n * 8}, {ubx, o_ub, n * 8}, {p, o_p, (size_t)B * np * 8}};
-  for (const Xfer& t : ins) {
+  struct Xfer { const void* user; size_t off, bytes, row; };
+  const Xfer ins[] = {{x0, o_x0, x0 ? (size_t)B * n * 8 : 0, n * 8}, {p, o_p, (size_t)B * np * 8, np * 8},
+                      {lbx, o_lb, n * 8, 0}, {ubx, o_ub, n * 8, 0}};
+  const Xfer outs[] = {{x, o_x, (size_t)B * n * 8, n * 8}, {f, o_f, (size_t)B * 8, 8}, {g, o_g, (size_t)B * ng * 8, ng * 8},
+                       {lam_g, o_lg, (size_t)B * ng * 8, ng * 8}, {lam_x, o_lx, (size_t)B * n * 8, n * 8},
+                       {status, o_st, (size_t)B * 4, 4}, {iters, o_it, (size_t)B * 4, 4}};
+  // pageable user memory goes through the pinned staging block (inputs now, outputs after the synchronise)
+  const char* in_src[4] = {nullptr, nullptr, nullptr, nullptr};
+  for (int i = 0; i < 4; ++i) {
+    const Xfer& t = ins[i];
     if (!t.user || t.bytes == 0) continue;
-    const void* src = t.user;
-    if (!is_pinned_host(t.user)) { std::memcpy(hp + t.off, t.user, t.bytes); src = hp + t.off; }
-    CUDA_OK(cudaMemcpyAsync(dp + t.off, src, t.bytes, cudaMemcpyHostToDevice, st));
+    in_src[i] = (const char*)t.user;
+    if (!is_pinned_host(t.user)) { std::memcpy(hp + t.off, t.user, t.bytes); in_src[i] = hp + t.off; }
   }
-  int rc = mpcv_solve(h, x0 ? (const double*)(dp + o_x0) : nullptr, (const double*)(dp + o_lb), (const double*)(dp + o_ub),
-                      (const double*)(dp + o_p), (double*)(dp + o_x), (double*)(dp + o_f), g ? (double*)(dp + o_g) : nullptr,
-                      lam_g ? (double*)(dp + o_lg) : nullptr, lam_x ? (double*)(dp + o_lx) : nullptr,
-                      (int32_t*)(dp + o_st), (int32_t*)(dp + o_it), B, st);
-  if (rc) return rc;
-  const Xfer outs[] = {{x, o_x, (size_t)B * n * 8}, {f, o_f, (size_t)B * 8}, {g, o_g, (size_t)B * ng * 8},
-                       {lam_g, o_lg, (size_t)B * ng * 8}, {lam_x, o_lx, (size_t)B * n * 8}, {status, o_st, (size_t)B * 4},
-                       {iters, o_it, (size_t)B * 4}};
+  char* out_dst[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool staged[7] = {false, false, false, false, false, false, false};
   for (int i = 0; i < 7; ++i) {
     const Xfer& t = outs[i];
     if (!t.user || t.bytes == 0) continue;
-    void* dst = const_cast<void*>(t.user);
-    if (!is_pinned_host(t.user)) { dst = hp + t.off; staged[i] = true; }
-    CUDA_OK(cudaMemcpyAsync(dst, dp + t.off, t.bytes, cudaMemcpyDeviceToHost, st));
+    out_dst[i] = (char*)const_cast<void*>(t.user);
+    if (!is_pinned_host(t.user)) { out_dst[i] = hp + t.off; staged[i] = true; }
   }
+  // the bounds are shared by the batch: copied up front.  The per-problem arrays are handed to the phase pipeline,
+  // which copies each pipe's share on that pipe's stream (H2D of one share under the solve of another, D2H of a
+  // finished share under the stragglers of the rest); any other layout copies them here, around the solve.
+  for (int i = 2; i < 4; ++i)
+    CUDA_OK(cudaMemcpyAsync(dp + ins[i].off, in_src[i], ins[i].bytes, cudaMemcpyHostToDevice, st));
+  mpcv_host_xfer xf = {};
+  for (int i = 0; i < 2; ++i) if (in_src[i]) xf.in[i] = {in_src[i], nullptr, dp + ins[i].off, ins[i].row};
+  for (int i = 0; i < 7; ++i) if (out_dst[i]) xf.out[i] = {nullptr, out_dst[i], dp + outs[i].off, outs[i].row};
+  const bool pipelined = h->layout == MPCV_LAYOUT_PHASED && !h->single && B > 0;
+  if (!pipelined)
+    for (int i = 0; i < 2; ++i)
+      if (in_src[i]) CUDA_OK(cudaMemcpyAsync(dp + ins[i].off, in_src[i], ins[i].bytes, cudaMemcpyHostToDevice, st));
+  h->host_xfer = pipelined ? &xf : nullptr;
+  h->host_xfer_done = false;
+  int rc = mpcv_solve(h, x0 ? (const double*)(dp + o_x0) : nullptr, (const double*)(dp + o_lb), (const double*)(dp + o_ub),
+                      (const double*)(dp + o_p), (double*)(dp + o_x), (double*)(dp + o_f), g ? (double*)(dp + o_g) : nullptr,
+                      lam_g ? (double*)(dp + o_lg) : nullptr, lam_x ? (double*)(dp + o_lx) : nullptr,
+                      (int32_t*)(dp + o_st), (int32_t*)(dp + o_it), B, st);
+  h->host_xfer = nullptr;
+  if (rc) return rc;
+  if (pipelined && !h->host_xfer_done) return mpcv_set_error(-EIO, "mpcv_solve_host: the phase pipeline did not take the host transfers");
+  if (!pipelined)
+    for (int i = 0; i < 7; ++i)
+      if (out_dst[i]) CUDA_OK(cudaMemcpyAsync(out_dst[i], dp + outs[i].off, outs[i].bytes, cudaMemcpyDeviceToHost, st));
   CUDA_OK(cudaStreamSynchronize(st));
   for (int i = 0; i < 7; ++i)
     if (staged[i]) std::memcpy(const_cast<void*>(outs[i].user), hp + outs[i].off, outs[i].bytes);

@@ -20,6 +20,14 @@ int mpcv_set_error(int code, const std::string& msg);
       return mpcv_set_error(-EIO, std::string(#call) + ": " + cudaGetErrorString(e__));     \
   } while (0)
 
+// Per-problem arrays of a host-pointer solve (mpcv_solve_host).  The phase pipeline copies them share by share on
+// the pipes' own streams, so that the transfers of one share run under the solve of another.
+struct mpcv_host_xfer {
+  struct Arr { const char* host_src; char* host_dst; char* dev; size_t row_bytes; };
+  Arr in[2];     // x0, p                                   (host_src -> dev)
+  Arr out[7];    // x, f, g, lam_g, lam_x, status, iters    (dev -> host_dst)
+};
+
 struct mpcv_handle {
   mpcv_spec spec;
   mpcv::Params P;
@@ -41,6 +49,8 @@ struct mpcv_handle {
   int64_t launches = 0;
   struct mpcv_phase_state* phase = nullptr;   // phase-kernel pipeline resources (mpcv_phase_inst.cu)
   int64_t phase_graph_launches = 0;
+  const mpcv_host_xfer* host_xfer = nullptr;   // set by mpcv_solve_host around its mpcv_solve call
+  bool host_xfer_done = false;                 // the launcher took care of the per-problem copies
 };
 
 // per-model entry points (defined once per model in mpcv_inst.cu, -DMPCV_INST_MODEL=<id>)

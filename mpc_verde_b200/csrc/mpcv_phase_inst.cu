@@ -390,8 +390,14 @@ static int launch_solve_phased(mpcv_handle* h, const SolveIO& io, long B, cudaSt
       PhasePipe& q = s->pipe[j];
       const cudaStream_t qs = j == 0 ? st : q.stream;
       if (j > 0) CUDA_OK(cudaStreamWaitEvent(qs, s->fork, 0));
+      if (const mpcv_host_xfer* xf = h->host_xfer)
+        for (const auto& t : xf->in)
+          if (t.host_src) CUDA_OK(cudaMemcpyAsync(t.dev + b0 * t.row_bytes, t.host_src + b0 * t.row_bytes, nb * t.row_bytes, cudaMemcpyHostToDevice, qs));
       ph_begin_kernel<<<1, 1, 0, qs>>>(q.ctrl, q.d_io, phase_sub_io(h, io, b0), (int)nb, ph_tail_below((int)nb));
       CUDA_OK(cudaGraphLaunch(q.exec, qs));
+      if (const mpcv_host_xfer* xf = h->host_xfer)
+        for (const auto& t : xf->out)
+          if (t.host_dst) CUDA_OK(cudaMemcpyAsync(t.host_dst + b0 * t.row_bytes, t.dev + b0 * t.row_bytes, nb * t.row_bytes, cudaMemcpyDeviceToHost, qs));
       h->launches += 6;    // begin + init chain + tail; the sweeps are counted from the device (mpcv_phase_sweeps)
       if (j > 0) {
         CUDA_OK(cudaEventRecord(q.done, qs));
@@ -399,14 +405,24 @@ static int launch_solve_phased(mpcv_handle* h, const SolveIO& io, long B, cudaSt
       }
     }
     h->phase_graph_launches++;
+    if (h->host_xfer) h->host_xfer_done = true;
     return 0;
   }
   // host-driven loop: one pipe over the whole batch (phase_pipes_for returns 1 when the environment asks for it;
   // after a graph failure re-lay the lists out for one pipe)
   if (K != 1) { if (int rc = phase_ensure(h, B, 1)) return rc; }
+  if (const mpcv_host_xfer* xf = h->host_xfer)
+    for (const auto& t : xf->in)
+      if (t.host_src) CUDA_OK(cudaMemcpyAsync(t.dev, t.host_src, B * t.row_bytes, cudaMemcpyHostToDevice, st));
   ph_begin_kernel<<<1, 1, 0, st>>>(s->pipe[0].ctrl, s->pipe[0].d_io, io, (int)B, ph_tail_below((int)B));
   h->launches++;
-  return phase_host_loop<Model>(h, st);
+  if (int rc = phase_host_loop<Model>(h, st)) return rc;
+  if (const mpcv_host_xfer* xf = h->host_xfer) {
+    for (const auto& t : xf->out)
+      if (t.host_dst) CUDA_OK(cudaMemcpyAsync(t.host_dst, t.dev, B * t.row_bytes, cudaMemcpyDeviceToHost, st));
+    h->host_xfer_done = true;
+  }
+  return 0;
 }
 
 // closed loop: per MPC step  prepare -> solve (graph) -> apply, all stream-ordered
