@@ -301,7 +301,7 @@ def main():
     traffic = None      # DRAM bytes of one solve launch from the committed ncu launch list (profiles/)
     try:
         if B == B_PER_GPU and args.layout in (S.LAYOUT_AUTO, S.LAYOUT_PHASED):
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1c_traffic.json")))["dram_bytes_per_solve_launch"]
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1d_traffic.json")))["dram_bytes_per_solve_launch"]
     except Exception:
         pass
     roofline = {
