@@ -287,7 +287,7 @@ def main():
     solver.disable_latency()
 
     # ---- roofline of the solve launch: ONE CUDA graph per step (init chain + a conditional WHILE node holding
-    # the 10-kernel iteration sweep); its duration is taken with CUDA events on the launching stream ----
+    # the 12-kernel iteration sweep, one graph per pipe); its duration is taken with CUDA events on the launching stream ----
     peak_tf, _ = mv.fp64_peak()
     kernel_ms = tk_ms / args.steps
     flops = iters_sum * FLOP_PER_ITER_C2

@@ -37,8 +37,11 @@
 // The sequential recursions run one thread per problem (every lane busy, coalesced rows of the blocked
 // slab); everything that is parallel over variables or intervals runs with 4-10x more threads so
 // that HBM latency is hidden by parallelism instead of being serialised inside one thread.
-// The whole solve is ONE CUDA graph whose iteration body sits in a conditional WHILE node, so
-// mpcv_solve stays asynchronous on the caller's stream (no host round trip per iteration).
+// The whole solve of a pipe is ONE CUDA graph whose iteration body sits in a conditional WHILE node, so
+// mpcv_solve stays asynchronous on the caller's stream (no host round trip per iteration).  A large batch is split
+// into several pipes — independent instances of this pipeline over contiguous shares of the batch, each with its own
+// lists, control block and graph on its own stream (mpcv_phase_inst.cu) — so that the phases of different shares overlap.
+// The warp-per-problem kernels (slow, tail) run on a shared-memory copy of their problem's workspace.
 //
 // The per-thread bodies below are plain functions shared by the CUDA kernels and by the CPU
 // development harness (tests/hostsim), which replays the same schedule with one lane per problem.
