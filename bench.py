@@ -143,7 +143,7 @@ def main():
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="problems per GPU per step")
     ap.add_argument("--layout", type=int, default=S.LAYOUT_AUTO)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--gather", default="inline", choices=["inline", "overlap"],
+    ap.add_argument("--gather", default="inline", choices=["inline", "overlap", "none"],
                     help="N>1: NCCL gather of the results in stream order after each solve, or on a side stream under the next solve")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -190,7 +190,7 @@ def main():
     gstream = torch.cuda.Stream(device=dev) if (world > 1 and args.gather == "overlap") else None
 
     def gather(sol):
-        if world == 1:
+        if world == 1 or args.gather == "none":      # "none": diagnostic (solve time per rank without any collective)
             return None
         st, it = solver._last
         if gstream is None:
@@ -249,6 +249,8 @@ def main():
     tk_ms = sum(a.elapsed_time(b) for a, b in evk)
     if rank == 0:
         sampler.stop_flag = True
+    print("rank %d: %.3f ms per step in the timed region, %.3f ms per solve" % (rank, t_ms / args.steps, tk_ms / args.steps),
+          file=sys.stderr)
     tt = torch.tensor([t_ms, tk_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
