@@ -178,6 +178,32 @@ def test_phase_pipes_split_the_batch_without_changing_results(mv, monkeypatch):
         assert np.abs(sol["f"] - out[0][0]["f"]).max() <= 1e-6 * (1 + np.abs(out[0][0]["f"]).max())
 
 
+def test_host_buffers_ride_the_pipes(mv, monkeypatch):
+    """mpcv_solve_host hands the per-problem arrays to the pipes, each share copied on its pipe's stream: page-locked
+    caller memory (copied in place), pageable memory (through the staging block) and device tensors (no copy) must
+    give the same bits, with ragged shares and every optional output requested."""
+    import torch
+    x0s, p = common.unicycle_batch(3001, seed=29)
+    monkeypatch.setenv("MPCV_PHASE_PIPE_MIN", "256")
+    monkeypatch.setenv("MPCV_PHASE_PIPES", "4")
+    solver = _solver(mv, problems.unicycle_multiple_shooting(), layout=S.LAYOUT_PHASED)
+    sp = solver.spec
+    lbx, ubx = problems.unicycle_bounds(sp, x_box=20.0)
+    w0 = problems.cold_start(sp, x0s)
+    keys = ("x", "f", "g", "lam_g", "lam_x")
+    pageable = solver(x0=w0, lbx=lbx, ubx=ubx, p=p, outputs=keys)
+    it_pageable = np.array(solver.stats()["iter_count"])
+    pinned = solver(x0=torch.as_tensor(w0).pin_memory(), lbx=lbx, ubx=ubx, p=torch.as_tensor(p).pin_memory(), outputs=keys)
+    pinned = {k: np.array(v) for k, v in pinned.items()}
+    dev = solver(x0=torch.as_tensor(w0).cuda(), lbx=torch.as_tensor(lbx).cuda(), ubx=torch.as_tensor(ubx).cuda(),
+                 p=torch.as_tensor(p).cuda(), outputs=keys)
+    assert solver.stats()["success"]
+    for k in keys:
+        assert np.array_equal(pageable[k], pinned[k]), k
+        assert np.array_equal(pageable[k], dev[k].cpu().numpy()), k
+    assert np.array_equal(it_pageable, np.array(solver.stats()["iter_count"]))
+
+
 @pytest.mark.parametrize("hostloop", [False, True])
 def test_phased_layout_equals_thread_layout(mv, hostloop, monkeypatch):
     """The phase-kernel pipeline (one CUDA graph with a conditional WHILE node, or the host-driven
