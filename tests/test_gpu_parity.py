@@ -178,6 +178,25 @@ def test_phase_pipes_split_the_batch_without_changing_results(mv, monkeypatch):
         assert np.abs(sol["f"] - out[0][0]["f"]).max() <= 1e-6 * (1 + np.abs(out[0][0]["f"]).max())
 
 
+def test_closed_loop_over_several_pipes(mv, monkeypatch):
+    """The batched closed loop (prepare -> solve -> apply per MPC step) with the per-step solve split over pipes: the
+    fork / join sits inside every step; the trajectories must not depend on the number of pipes."""
+    x0s, _ = common.unicycle_batch(1500, seed=31)
+    target = np.tile([10.0, 10.0, 0.0], (x0s.shape[0], 1))
+    monkeypatch.setenv("MPCV_PHASE_PIPE_MIN", "256")
+    out = []
+    for pipes in ("1", "3"):
+        monkeypatch.setenv("MPCV_PHASE_PIPES", pipes)
+        solver = _solver(mv, problems.unicycle_multiple_shooting(), layout=S.LAYOUT_PHASED)
+        lbx, ubx = problems.unicycle_bounds(solver.spec)
+        out.append(solver.closed_loop(x0s, target, None, lbx, ubx, n_steps=6, warm_mode=S.WARM_SHIFT, stop_radius=0.1))
+    a, b = out
+    assert np.all(a["status"] == 0) and np.all(b["status"] == 0)
+    assert np.array_equal(a["steps"], b["steps"])
+    assert np.abs(a["controls"] - b["controls"]).max() <= 1e-7
+    assert np.abs(a["states"] - b["states"]).max() <= 1e-7
+
+
 def test_host_buffers_ride_the_pipes(mv, monkeypatch):
     """mpcv_solve_host hands the per-problem arrays to the pipes, each share copied on its pipe's stream: page-locked
     caller memory (copied in place), pageable memory (through the staging block) and device tensors (no copy) must
