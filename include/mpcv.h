@@ -36,7 +36,9 @@
  *   - Return 0 on success, negative errno-style code on failure;
  *     mpcv_last_error() holds a message.  Nothing throws across the ABI.
  *   - Per-problem solver status mirrors IPOPT's ApplicationReturnStatus.
- *   - One handle per GPU; a handle is not thread-safe.
+ *   - One handle per GPU; a handle is not thread-safe, and calls through one handle are ordered: a call
+     issued on another stream first waits (on the device) for the previous call of the handle to finish,
+     because the workspaces, lists and graphs are owned by the handle.
  *
  * Decision-vector layouts (identical to the reference scripts')
  *   multiple shooting (multiple_shooting_casadi.py:116-178):
@@ -106,15 +108,28 @@ enum {
                                multiple_shooting_casadi.py:284-287, single_shooting_v1.py:173 */
 };
 
+/* closed-loop flags (mpcv_loop_args.flags) */
+enum {
+  MPCV_LOOP_X0_FROM_PREDICTION = 1,  /* next x0 = the solver's predicted x_1 instead of the plant state:
+                                        solver.fixvar("x",0,solver.var["x",1]), Trajectory_tracking.py:111-112 */
+  MPCV_LOOP_PTRAJ_WINDOWS = 2        /* ptraj holds one full horizon window per MPC step, [B x n_steps x N x nps]
+                                        (the par[:, k, t] tables of the scripts), instead of one trajectory
+                                        [B x (n_steps+N) x nps] read through a sliding window */
+};
+
 /* kernel layout selection */
 enum {
   MPCV_LAYOUT_AUTO = 0,
   MPCV_LAYOUT_THREAD = 1,   /* one problem per thread, SoA workspace in HBM/L2 */
   MPCV_LAYOUT_WARP = 2,     /* one warp per problem, stage-parallel, shared-memory workspace */
-  MPCV_LAYOUT_PHASED = 3    /* batch-synchronous phase kernels over the thread layout's workspace: one
+  MPCV_LAYOUT_PHASED = 3,   /* batch-synchronous phase kernels over the thread layout's workspace: one
                                thread per (problem, interval) for the derivative / trial sweeps, one
                                thread per problem for the Riccati recursion, active-list compaction,
                                one CUDA graph (conditional WHILE) per solve; multiple shooting only */
+  MPCV_LAYOUT_RESIDENT = 4  /* persistent CTAs that keep the workspaces of their problems in shared memory and walk
+                               the phases of an iteration in lock step; finished problems are replaced from a
+                               global queue (continuous batching).  Only x0 / p in and x / f out touch HBM.
+                               What MPCV_LAYOUT_AUTO picks when an SM holds >= 8 problems; multiple shooting only */
 };
 
 typedef struct mpcv_spec {
@@ -141,6 +156,11 @@ typedef struct mpcv_spec {
   double  constr_viol_tol;           /* 1e-4 */
   double  compl_inf_tol;             /* 1e-4 */
   double  extra[4];                  /* model constants: FRENET: [L, Nt+1 divisor, -, -] */
+  /* acceptable-level termination (opts of Casadi/single_shooting_v1.py:121-129); 0 = IPOPT default */
+  double  acceptable_tol;             /* 1e-6 */
+  int32_t acceptable_iter;            /* 15; negative switches the test off */
+  int32_t reserved_;
+  double  acceptable_obj_change_tol;  /* 1e20 */
 } mpcv_spec;
 
 typedef struct mpcv_handle mpcv_handle;
@@ -193,12 +213,76 @@ int mpcv_closed_loop(mpcv_handle* h, const double* x_init, const double* pglob,
                      double* out_states, double* out_controls, int32_t* out_steps,
                      int32_t* out_iters, int32_t* out_status, int64_t B, void* stream);
 
+/* Extended closed loop: everything mpcv_closed_loop takes, plus per-step model parameters (the LTV scripts
+   re-discretise Ac(c[t]) / Ac(vref[t]) every step: Trjectory_tracking_le_LTV.py:126-143,
+   Trajectory_tracking_dynamic_model.py:119-141), the x0-from-prediction mode of the MPCTools loops, per-step
+   parameter windows, and the histories every script keeps: the predicted horizon of every
+   solve (`cat_states`, single_shooting_v1.py:185-188) and the duration of every MPC step (`times`, :209-212).
+   Scenarios whose loop has stopped (stop_radius) are no longer solved.  Device pointers; unused ones NULL. */
+typedef struct mpcv_loop_args {
+  const double* x_init;        /* [B x nx] */
+  const double* pglob;         /* [B x npg] constant model parameters */
+  const double* pglob_traj;    /* [B x n_steps x npg] model parameters of step t (overrides pglob) */
+  const double* ptraj;         /* [B x (n_steps+N) x nps], or [B x n_steps x N x nps] with MPCV_LOOP_PTRAJ_WINDOWS */
+  const double* lbx;           /* [n_var] */
+  const double* ubx;           /* [n_var] */
+  int32_t n_steps, warm_mode, flags, reserved_;
+  double stop_radius;
+  double* out_states;          /* [B x (n_steps+1) x nx] plant states */
+  double* out_controls;        /* [B x n_steps x nu] applied controls */
+  int32_t* out_steps;          /* [B] */
+  int32_t* out_iters;          /* [B] */
+  int32_t* out_status;         /* [B] */
+  double* out_horizons;        /* [B x n_steps x (N+1) x nx] predicted states of every solve */
+  long long* out_step_ns;      /* [n_steps] device-timer nanoseconds of every MPC step of the batch */
+} mpcv_loop_args;
+int mpcv_closed_loop_ex(mpcv_handle* h, const mpcv_loop_args* a, int64_t B, void* stream);
+
+/* Batched solve with per-problem bounds: lbx / ubx are [B x n_var] (the reference call takes one lbx / ubx per
+   solve, single_shooting_v1.py:174-181, so a batch of calls may carry different boxes).  lbg / ubg of the reference
+   call are fixed by the transcription; lam_p is not provided.  Otherwise as mpcv_solve. */
+int mpcv_solve_bounds(mpcv_handle* h, const double* x0, const double* lbx, const double* ubx, const double* p,
+                      double* x, double* f, double* g, double* lam_g, double* lam_x, int32_t* status,
+                      int32_t* iters, int64_t B, void* stream);
+
 /* Batched exact zero-order hold (replaces mpc.util.c2d, Inverted_pendulum/inverted_pendulum_single_shooting_mpctools.py:24,
    Trajectory Tracking/Trjectory_tracking_le_LTV.py:126-133, Trajectory_tracking_dynamic_model.py:134):
    [A Bd; 0 I] = expm([Ac Bc; 0 0] dt) for B systems.  Ac [B x n x n], Bc [B x n x nu] -> A [B x n x n],
    Bd [B x n x nu], row-major device pointers; n + nu <= 6. */
 int mpcv_c2d(int32_t n, int32_t nu, double dt, const double* Ac, const double* Bc, double* A, double* Bd,
              int64_t B, void* stream);
+
+/* ---- reference-trajectory pipeline on the device -------------------------------------
+   The scripts build their per-stage parameter tables and per-step models in nested Python loops right before the
+   solve; these entry points build them for B scenarios at once, in HBM, in the layouts mpcv_closed_loop_ex reads.
+   A scenario is the base path (x, y) [nsim] stretched by scale[b] = (sx, sy) (NULL: unscaled).  Device pointers. */
+
+/* par[:, k, t] of the lateral-error trackers (Trajectory_tracking_lateral_error.py:94-116, Phiref.py:124-155):
+   (y_ref, phi_ref, r_ref, delta_ref) -> pwin [B x nsim x Nt x 4]  (MPCV_LOOP_PTRAJ_WINDOWS layout) */
+int mpcv_ref_lateral(const double* x, const double* y, int32_t nsim, const double* scale, int32_t Nt, double Delta,
+                     double ar, double br, double* pwin, int64_t B, void* stream);
+/* p[k, :] of the Frenet bicycle (test2.py:79-100; p[2] / p[3] swapped as in the script) -> pwin [B x n_steps x Nt x 4] */
+int mpcv_ref_frenet(const double* x, const double* y, const double* vdes, int32_t nsim, const double* scale, int32_t Nt,
+                    double Delta, int32_t n_steps, double* pwin, int64_t B, void* stream);
+/* (x, y, theta, v, omega) references of the unicycle tracker cut from a path sampled every dt (central differences,
+   v / omega clipped to the control box) -> ptraj [B x T x 5]  (sliding-window layout) */
+int mpcv_ref_unicycle_path(const double* x, const double* y, int32_t T, const double* scale, double dt, double vmax,
+                           double wmax, double* ptraj, int64_t B, void* stream);
+/* the circle reference of Trajectory_tracking.py:84-97 -> ptraj [T x 5] */
+int mpcv_ref_circle(int32_t T, double Delta, double* ptraj, void* stream);
+/* lane_change.py:5-79: the base path (a, b, c) [n0] extended by arcs and straights -> (xt, yt, c2) [*n_out], the
+   columns of out.csv.  a_end / b_end: the last base sample (host values).  xt = NULL only sizes the output. */
+int mpcv_path_lane_change_ext(const double* a, const double* b, const double* c, int32_t n0, double a_end, double b_end,
+                              double v, double dt, double* xt, double* yt, double* c2, int32_t capacity, int32_t* n_out,
+                              void* stream);
+/* per-step exact ZOH of the LTV models -> pglob_traj [B x n_steps x npg] (= [A row-major, B]):
+   lateral-error bicycle, u_ref = c[t] * spd[b] (Trjectory_tracking_le_LTV.py:126-133), npg = 12;
+   dynamic bicycle in v = v[t] (per_scenario: v is [B x T]) with params = (m, a, b, Ca, Jz) or NULL for the script's
+   (Trajectory_tracking_dynamic_model.py:37-43,119-134, the A34 precedence as written), npg = 20 */
+int mpcv_ltv_lateral(const double* c, int32_t T, const double* spd, double ar, double br, double dt, int32_t n_steps,
+                     double* pglob_traj, int64_t B, void* stream);
+int mpcv_ltv_dynbike(const double* v, int32_t T, int32_t per_scenario, const double* params, double dt, int32_t n_steps,
+                     double* pglob_traj, int64_t B, void* stream);
 
 /* Measured FP64 FMA peak of the current device in TFLOP/s (register-resident DFMA chains);
    the roofline denominator of bench.py. */

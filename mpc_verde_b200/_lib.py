@@ -33,7 +33,25 @@ SIGNATURES = {
     "mpcv_launch_count": (C.c_int64, [_V]),
     "mpcv_c2d": (C.c_int, [C.c_int32, C.c_int32, C.c_double, _V, _V, _V, _V, C.c_int64, _V]),
     "mpcv_phase_sweeps": (C.c_int, [_V, C.POINTER(C.c_int32), C.POINTER(C.c_int64), _V]),
+    "mpcv_closed_loop_ex": (C.c_int, [_V, _V, C.c_int64, _V]),
+    "mpcv_solve_bounds": (C.c_int, [_V] + [_V] * 4 + [_V] * 5 + [_V, _V, C.c_int64, _V]),
+    "mpcv_ref_lateral": (C.c_int, [_V, _V, C.c_int32, _V, C.c_int32, C.c_double, C.c_double, C.c_double, _V, C.c_int64, _V]),
+    "mpcv_ref_frenet": (C.c_int, [_V, _V, _V, C.c_int32, _V, C.c_int32, C.c_double, C.c_int32, _V, C.c_int64, _V]),
+    "mpcv_ref_unicycle_path": (C.c_int, [_V, _V, C.c_int32, _V, C.c_double, C.c_double, C.c_double, _V, C.c_int64, _V]),
+    "mpcv_ref_circle": (C.c_int, [C.c_int32, C.c_double, _V, _V]),
+    "mpcv_path_lane_change_ext": (C.c_int, [_V, _V, _V, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, _V, _V, _V,
+                                            C.c_int32, C.POINTER(C.c_int32), _V]),
+    "mpcv_ltv_lateral": (C.c_int, [_V, C.c_int32, _V, C.c_double, C.c_double, C.c_double, C.c_int32, _V, C.c_int64, _V]),
+    "mpcv_ltv_dynbike": (C.c_int, [_V, C.c_int32, C.c_int32, _V, C.c_double, C.c_int32, _V, C.c_int64, _V]),
 }
+
+
+class LoopArgs(C.Structure):
+    """ctypes mirror of `mpcv_loop_args` (include/mpcv.h)."""
+    _fields_ = [("x_init", _V), ("pglob", _V), ("pglob_traj", _V), ("ptraj", _V), ("lbx", _V), ("ubx", _V),
+                ("n_steps", C.c_int32), ("warm_mode", C.c_int32), ("flags", C.c_int32), ("reserved_", C.c_int32),
+                ("stop_radius", C.c_double), ("out_states", _V), ("out_controls", _V), ("out_steps", _V),
+                ("out_iters", _V), ("out_status", _V), ("out_horizons", _V), ("out_step_ns", _V)]
 
 
 class MpcvError(RuntimeError):

@@ -5,6 +5,7 @@
 #include <cstring>
 
 #include "mpcv_host.h"
+#include "mpcv_c2d.cuh"
 
 using namespace mpcv;
 
@@ -55,72 +56,18 @@ __global__ void fp64_peak_kernel(double* out, int iters) {
 }
 
 
-// Exact zero-order hold of xdot = Ac x + Bc u, batched: [A B; 0 I] = expm([Ac Bc; 0 0] dt) — what
-// mpc.util.c2d computes on the host for every scenario / every step of the LTV scripts
-// (Inverted_pendulum/inverted_pendulum_single_shooting_mpctools.py:24, Trjectory_tracking_le_LTV.py:126-133,
-// Trajectory_tracking_dynamic_model.py:134).  One thread per system; scaling and squaring around a
-// degree-18 Taylor polynomial evaluated by Horner's rule (||M / 2^s||_1 <= 1/4, so truncation is far below
-// one ulp; the stiff dynamic bicycle needs s = 9 squarings).
 template <int S>
 __global__ void c2d_kernel(int n, int nu, double dt, const double* Ac, const double* Bc, double* A, double* Bd, long B) {
   const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  double M[S * S], E[S * S], T[S * S];
+  double M[S * S], E[S * S];
 #pragma unroll
   for (int i = 0; i < S * S; ++i) M[i] = 0.0;
   for (int i = 0; i < n; ++i) {
     for (int j = 0; j < n; ++j) M[i * S + j] = Ac[(b * n + i) * n + j] * dt;
     for (int j = 0; j < nu; ++j) M[i * S + n + j] = Bc[(b * n + i) * nu + j] * dt;
   }
-  double nrm = 0.0;
-#pragma unroll
-  for (int j = 0; j < S; ++j) {
-    double c = 0.0;
-#pragma unroll
-    for (int i = 0; i < S; ++i) c += fabs(M[i * S + j]);
-    nrm = fmax(nrm, c);
-  }
-  int s = 0;
-  while (nrm > 0.25 && s < 60) { nrm *= 0.5; ++s; }
-  const double sc = ldexp(1.0, -s);
-#pragma unroll
-  for (int i = 0; i < S * S; ++i) M[i] *= sc;
-  // Horner: E = I + M (I + M/2 (I + M/3 (... (I + M/18))))
-#pragma unroll
-  for (int i = 0; i < S * S; ++i) E[i] = 0.0;
-#pragma unroll
-  for (int i = 0; i < S; ++i) E[i * S + i] = 1.0;
-  for (int k = 18; k >= 1; --k) {
-    const double rk = 1.0 / k;
-#pragma unroll
-    for (int i = 0; i < S; ++i) {
-#pragma unroll
-      for (int j = 0; j < S; ++j) {
-        double v = 0.0;
-#pragma unroll
-        for (int l = 0; l < S; ++l) v += M[i * S + l] * E[l * S + j];
-        T[i * S + j] = v * rk;
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < S * S; ++i) E[i] = T[i];
-#pragma unroll
-    for (int i = 0; i < S; ++i) E[i * S + i] += 1.0;
-  }
-  for (int q = 0; q < s; ++q) {
-#pragma unroll
-    for (int i = 0; i < S; ++i) {
-#pragma unroll
-      for (int j = 0; j < S; ++j) {
-        double v = 0.0;
-#pragma unroll
-        for (int l = 0; l < S; ++l) v += E[i * S + l] * E[l * S + j];
-        T[i * S + j] = v;
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < S * S; ++i) E[i] = T[i];
-  }
+  mpcv::expm_small<S>(M, E);
   for (int i = 0; i < n; ++i) {
     for (int j = 0; j < n; ++j) A[(b * n + i) * n + j] = E[i * S + j];
     for (int j = 0; j < nu; ++j) Bd[(b * n + i) * nu + j] = E[i * S + n + j];
@@ -166,6 +113,7 @@ void mpcv_spec_defaults(mpcv_spec* s) {
   s->bound_push = 1e-2; s->bound_frac = 1e-2; s->bound_relax_factor = 1e-8;
   s->nlp_scaling_max_gradient = 100.0;
   s->dual_inf_tol = 1.0; s->constr_viol_tol = 1e-4; s->compl_inf_tol = 1e-4;
+  s->acceptable_tol = 1e-6; s->acceptable_iter = 15; s->acceptable_obj_change_tol = 1e20;
 }
 
 int mpcv_dims(const mpcv_spec* s, int32_t* nx, int32_t* nu, int32_t* n_var, int32_t* n_g, int32_t* n_p,
@@ -195,15 +143,28 @@ mpcv_handle* mpcv_create(const mpcv_spec* s) {
   h->single = s->shooting == MPCV_SHOOTING_SINGLE;
   h->P = params_from_spec(*s);
   if (create_impl(h) != 0) { delete h; return nullptr; }
+  if (s->ntu > 0 && !h->has_uprev) {
+    // move blocking pins u_k = u_{k-1}: only the models that carry u_prev in their state can do that
+    mpcv_set_error(-EINVAL, "ntu > 0 needs a model with u_prev in its state (MPCV_MODEL_LINEAR3_DU / LINEAR4_DU / FRENET_BICYCLE)");
+    delete h;
+    return nullptr;
+  }
+  h->knobs = mpcv_knobs_from_env();
   cudaGetDevice(&h->device);
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, h->device) != cudaSuccess) { mpcv_set_error(-EIO, "cudaGetDeviceProperties"); delete h; return nullptr; }
   h->sm_count = prop.multiProcessorCount;
   h->max_smem_optin = prop.sharedMemPerBlockOptin;
+  h->smem_per_sm = prop.sharedMemPerMultiprocessor;
   h->layout = s->layout;
+  // AUTO: the slab pipeline for multiple shooting, one thread per problem for single shooting.  The CTA-resident
+  // layout is opt-in: it cuts the DRAM traffic of a solve 480x but is latency-bound (profiles/r2b_*).
+  const int res_slots = mpcv_phase_vtable_of(s->model)->res_slots_per_sm(h);
   if (h->layout == MPCV_LAYOUT_AUTO) h->layout = h->single ? MPCV_LAYOUT_THREAD : MPCV_LAYOUT_PHASED;
+  if (h->layout == MPCV_LAYOUT_RESIDENT && res_slots < 1) h->layout = MPCV_LAYOUT_PHASED;
   if (h->single) h->layout = MPCV_LAYOUT_THREAD;
-  if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+  if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->last_done, cudaEventDisableTiming) != cudaSuccess) {
     mpcv_set_error(-EIO, "cudaStreamCreate"); delete h; return nullptr;
   }
   return h;
@@ -216,6 +177,7 @@ void mpcv_destroy(mpcv_handle* h) {
   if (h->hpin) cudaFreeHost(h->hpin);
   if (h->dstage) cudaFree(h->dstage);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
+  if (h->last_done) cudaEventDestroy(h->last_done);
   delete h;
 }
 
@@ -237,40 +199,88 @@ int mpcv_set_latency_buffer(mpcv_handle* h, long long* dev_ns) {
   return 0;
 }
 
+// Every call reuses device state owned by the handle (workspace slabs, lists, control blocks, graphs, staging):
+// a call first makes its stream wait for the end of the handle's previous call, and records its own end.
+// The handle belongs to the device it was created on.
+static int call_begin(mpcv_handle* h, cudaStream_t st, const char* what) {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev != h->device)
+    return mpcv_set_error(-EINVAL, std::string(what) + ": the handle was created on device " + std::to_string(h->device) +
+                                       ", the current device is " + std::to_string(dev));
+  CUDA_OK(cudaStreamWaitEvent(st, h->last_done, 0));
+  return 0;
+}
+static int call_end(mpcv_handle* h, cudaStream_t st, int rc) {
+  // (recorded on failure too: whatever was enqueued before the error still uses the handle's buffers)
+  if (cudaEventRecord(h->last_done, st) != cudaSuccess && rc == 0) return mpcv_set_error(-EIO, "cudaEventRecord");
+  return rc;
+}
+
+static int solve_impl(mpcv_handle* h, const SolveIO& io, int64_t B, cudaStream_t st, const char* what) {
+  if (int rc = call_begin(h, st, what)) return rc;
+  return call_end(h, st, vtable_of(h->spec.model)->solve(h, io, (long)B, st));
+}
+
 int mpcv_solve(mpcv_handle* h, const double* x0, const double* lbx, const double* ubx, const double* p,
                double* x, double* f, double* g, double* lam_g, double* lam_x, int32_t* status, int32_t* iters,
                int64_t B, void* stream) {
   if (!h || !lbx || !ubx || !p) return mpcv_set_error(-EINVAL, "mpcv_solve: null argument");
   SolveIO io{x0, lbx, ubx, p, x, f, g, lam_g, lam_x, status, iters, h->latency_ns};
-  cudaStream_t st = (cudaStream_t)stream;
-  return vtable_of(h->spec.model)->solve(h, io, (long)B, st);
+  return solve_impl(h, io, B, (cudaStream_t)stream, "mpcv_solve");
+}
+
+int mpcv_solve_bounds(mpcv_handle* h, const double* x0, const double* lbx, const double* ubx, const double* p,
+                      double* x, double* f, double* g, double* lam_g, double* lam_x, int32_t* status,
+                      int32_t* iters, int64_t B, void* stream) {
+  if (!h || !lbx || !ubx || !p) return mpcv_set_error(-EINVAL, "mpcv_solve_bounds: null argument");
+  SolveIO io{x0, lbx, ubx, p, x, f, g, lam_g, lam_x, status, iters, h->latency_ns};
+  io.bstride = h->n_var;
+  return solve_impl(h, io, B, (cudaStream_t)stream, "mpcv_solve_bounds");
 }
 
 int mpcv_rollout(mpcv_handle* h, const double* p, const double* U, double* X, double* q, int64_t B, void* stream) {
   if (!h || !p || !U || !X) return mpcv_set_error(-EINVAL, "mpcv_rollout: null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  return vtable_of(h->spec.model)->rollout(h, p, U, X, q, (long)B, st);
+  if (int rc = call_begin(h, st, "mpcv_rollout")) return rc;
+  return call_end(h, st, vtable_of(h->spec.model)->rollout(h, p, U, X, q, (long)B, st));
 }
 
 int mpcv_stage_derivs(mpcv_handle* h, const double* z, const double* pstage, const double* lam, double* xn,
                       double* A, double* Bm, double* q, double* grad, double* H, int64_t B, void* stream) {
   if (!h || !z || !lam) return mpcv_set_error(-EINVAL, "mpcv_stage_derivs: null argument");
   cudaStream_t st = (cudaStream_t)stream;
-  return vtable_of(h->spec.model)->derivs(h, z, pstage, lam, xn, A, Bm, q, grad, H, (long)B, st);
+  if (int rc = call_begin(h, st, "mpcv_stage_derivs")) return rc;
+  return call_end(h, st, vtable_of(h->spec.model)->derivs(h, z, pstage, lam, xn, A, Bm, q, grad, H, (long)B, st));
+}
+
+int mpcv_closed_loop_ex(mpcv_handle* h, const mpcv_loop_args* a, int64_t B, void* stream) {
+  if (!h || !a || !a->x_init || !a->lbx || !a->ubx || !a->out_states || !a->out_controls)
+    return mpcv_set_error(-EINVAL, "mpcv_closed_loop: null argument");
+  if (h->nps > 0 && !a->ptraj) return mpcv_set_error(-EINVAL, "mpcv_closed_loop: ptraj required for this model");
+  if (h->npg > 0 && !a->pglob && !a->pglob_traj)
+    return mpcv_set_error(-EINVAL, "mpcv_closed_loop: pglob or pglob_traj required for this model");
+  if (a->n_steps < 0) return mpcv_set_error(-EINVAL, "mpcv_closed_loop: n_steps < 0");
+  LoopIO io{a->x_init, a->pglob, a->ptraj, a->lbx, a->ubx, a->out_states, a->out_controls, a->out_steps, a->out_iters,
+            a->out_status, a->n_steps, a->warm_mode, a->stop_radius};
+  io.pglob_traj = a->pglob_traj;
+  io.out_horizons = a->out_horizons;
+  io.out_step_ns = a->out_step_ns;
+  io.flags = a->flags;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = call_begin(h, st, "mpcv_closed_loop")) return rc;
+  return call_end(h, st, vtable_of(h->spec.model)->loop(h, io, (long)B, st));
 }
 
 int mpcv_closed_loop(mpcv_handle* h, const double* x_init, const double* pglob, const double* ptraj,
                      const double* lbx, const double* ubx, int32_t n_steps, int32_t warm_mode, double stop_radius,
                      double* out_states, double* out_controls, int32_t* out_steps, int32_t* out_iters,
                      int32_t* out_status, int64_t B, void* stream) {
-  if (!h || !x_init || !lbx || !ubx || !out_states || !out_controls)
-    return mpcv_set_error(-EINVAL, "mpcv_closed_loop: null argument");
-  if (h->nps > 0 && !ptraj) return mpcv_set_error(-EINVAL, "mpcv_closed_loop: ptraj required for this model");
-  if (h->npg > 0 && !pglob) return mpcv_set_error(-EINVAL, "mpcv_closed_loop: pglob required for this model");
-  LoopIO io{x_init, pglob, ptraj, lbx, ubx, out_states, out_controls, out_steps, out_iters, out_status,
-            n_steps, warm_mode, stop_radius};
-  cudaStream_t st = (cudaStream_t)stream;
-  return vtable_of(h->spec.model)->loop(h, io, (long)B, st);
+  mpcv_loop_args a = {};
+  a.x_init = x_init; a.pglob = pglob; a.ptraj = ptraj; a.lbx = lbx; a.ubx = ubx;
+  a.n_steps = n_steps; a.warm_mode = warm_mode; a.stop_radius = stop_radius;
+  a.out_states = out_states; a.out_controls = out_controls; a.out_steps = out_steps; a.out_iters = out_iters;
+  a.out_status = out_status;
+  return mpcv_closed_loop_ex(h, &a, B, stream);
 }
 
 // ---- host-pointer variant: H2D from pinned staging, solve, D2H, synchronise ---------------
@@ -345,7 +355,7 @@ int mpcv_solve_host(mpcv_handle* h, const double* x0, const double* lbx, const d
   mpcv_host_xfer xf = {};
   for (int i = 0; i < 2; ++i) if (in_src[i]) xf.in[i] = {in_src[i], nullptr, dp + ins[i].off, ins[i].row};
   for (int i = 0; i < 7; ++i) if (out_dst[i]) xf.out[i] = {nullptr, out_dst[i], dp + outs[i].off, outs[i].row};
-  const bool pipelined = h->layout == MPCV_LAYOUT_PHASED && !h->single && B > 0;
+  const bool pipelined = (h->layout == MPCV_LAYOUT_PHASED || h->layout == MPCV_LAYOUT_RESIDENT) && !h->single && B > 0;
   if (!pipelined)
     for (int i = 0; i < 2; ++i)
       if (in_src[i]) CUDA_OK(cudaMemcpyAsync(dp + ins[i].off, in_src[i], ins[i].bytes, cudaMemcpyHostToDevice, st));

@@ -34,6 +34,9 @@ struct SolveIO {
   int* status;         // [B]
   int* iters;          // [B]
   long long* ns;       // [B] per-problem latency (globaltimer), optional
+  long bstride = 0;            // 0: lbx / ubx are [n], shared by the batch; n: per-problem rows [B, n]
+  const int* index = nullptr;  // device, optional: I/O row of queue entry e (closed loops solve only live scenarios)
+  const int* count = nullptr;  // device, optional: number of queue entries (overrides B)
 };
 
 template <class Model, bool SINGLE, int LANES, class WS>
@@ -62,7 +65,7 @@ MPCV_D void solve_problem(const Params& P, const Layout& L, WS ws, Grp<LANES> g,
   const int np = NH + L.N * Model::NPS;
   for (int i = g.lane; i < L.n; i += LANES) ws[L.w + i] = io.x0 ? io.x0[b * L.n + i] : 0.0;
   for (int i = g.lane; i < NH; i += LANES) ws[L.par + i] = io.p[b * np + i];
-  Ipm<Model, SINGLE, LANES, WS> ipm(P, L, ws, g, io.lbx, io.ubx);
+  Ipm<Model, SINGLE, LANES, WS> ipm(P, L, ws, g, io.lbx + b * io.bstride, io.ubx + b * io.bstride);
   if (Model::NPS > 0) ipm.ps_base += stager.load(ws, L.par + NH, io.p + b * np + NH, L.N * Model::NPS, g);
   g.sync();
   const SolveInfo info = ipm.solve();
@@ -82,6 +85,10 @@ struct LoopIO {
   int* out_status;        // [B]
   int n_steps, warm_mode;
   double stop_radius;
+  const double* pglob_traj = nullptr;   // [B, n_steps, npg] per-step model parameters (LTV), overrides pglob
+  double* out_horizons = nullptr;       // [B, n_steps, N+1, nx] predicted states of every solve
+  long long* out_step_ns = nullptr;     // [n_steps] device-timer duration of every MPC step (phased / resident layouts)
+  int flags = 0;                        // MPCV_LOOP_*
 };
 
 template <class Model, bool SINGLE, int LANES, class WS, class Stager = PlainStager>
@@ -89,10 +96,10 @@ MPCV_D void closed_loop_problem(const Params& P, const Layout& L, WS ws, Grp<LAN
                                 const Stager& stager = Stager()) {
   constexpr int NX = Model::NX, NU = Model::NU, NZ = NX + NU;
   const int N = L.N, lane = g.lane;
-  double state[NX];
+  double state[NX], xctrl[NX];    // plant state; the controller's x0 (the same unless MPCV_LOOP_X0_FROM_PREDICTION)
 #pragma unroll
-  for (int i = 0; i < NX; ++i) state[i] = io.x_init[b * NX + i];
-  for (int i = lane; i < Model::NPG; i += LANES) ws[L.par + NX + i] = io.pglob[b * Model::NPG + i];
+  for (int i = 0; i < NX; ++i) xctrl[i] = state[i] = io.x_init[b * NX + i];
+  if (io.pglob) for (int i = lane; i < Model::NPG; i += LANES) ws[L.par + NX + i] = io.pglob[b * Model::NPG + i];
   double* os = io.out_states + b * (long)(io.n_steps + 1) * NX;
   double* oc = io.out_controls + b * (long)io.n_steps * NU;
   if (lane == 0) {
@@ -113,6 +120,13 @@ MPCV_D void closed_loop_problem(const Params& P, const Layout& L, WS ws, Grp<LAN
   int steps = 0, iters_total = 0, worst = 0;
   Ipm<Model, SINGLE, LANES, WS> ipm(P, L, ws, g, io.lbx, io.ubx);
   for (int t = 0; t < io.n_steps; ++t) {
+    if (io.pglob_traj) {
+      // LTV: the model of step t (Trjectory_tracking_le_LTV.py:126-143 re-discretises Ac(c[t]) every step)
+      g.sync();
+      for (int i = lane; i < Model::NPG; i += LANES)
+        ws[L.par + NX + i] = io.pglob_traj[(b * (long)io.n_steps + t) * Model::NPG + i];
+      g.sync();
+    }
     if (io.stop_radius > 0.0 && Model::NPG >= NX) {
       double d2 = 0.0;
 #pragma unroll
@@ -121,12 +135,14 @@ MPCV_D void closed_loop_problem(const Params& P, const Layout& L, WS ws, Grp<LAN
     }
     if (lane == 0) {
 #pragma unroll
-      for (int i = 0; i < NX; ++i) ws[L.par + i] = state[i];
+      for (int i = 0; i < NX; ++i) ws[L.par + i] = xctrl[i];
     }
     if (Model::NPS > 0) {
       // horizon window p[t..t+N) of this scenario's reference trajectory (overlapping slices of
-      // one array: nothing is materialised per step)
-      const double* src = io.ptraj + (b * (long)(io.n_steps + N) + t) * Model::NPS;
+      // one array: nothing is materialised per step), or the step's own window table
+      const double* src = (io.flags & MPCV_LOOP_PTRAJ_WINDOWS)
+                              ? io.ptraj + (b * (long)io.n_steps + t) * (long)N * Model::NPS
+                              : io.ptraj + (b * (long)(io.n_steps + N) + t) * Model::NPS;
       ipm.ps_base = L.par + NX + Model::NPG + stager.load(ws, L.par + NX + Model::NPG, src, N * Model::NPS, g);
     }
     if (io.warm_mode == MPCV_WARM_COLD) {
@@ -136,7 +152,7 @@ MPCV_D void closed_loop_problem(const Params& P, const Layout& L, WS ws, Grp<LAN
       if (!SINGLE) {
         for (int k = lane; k <= N; k += LANES) {
 #pragma unroll
-          for (int i = 0; i < NX; ++i) ws[L.w + k * NZ + i] = state[i];
+          for (int i = 0; i < NX; ++i) ws[L.w + k * NZ + i] = xctrl[i];
         }
       }
     }
@@ -150,6 +166,15 @@ MPCV_D void closed_loop_problem(const Params& P, const Layout& L, WS ws, Grp<LAN
     double u0[NU];
 #pragma unroll
     for (int i = 0; i < NU; ++i) u0[i] = ws[L.w + ipm.iu(0, i)];
+    if (io.out_horizons) {
+      // predicted horizon of this solve (cat_states of single_shooting_v1.py:185-188)
+      double* oh = io.out_horizons + (b * (long)io.n_steps + t) * (long)(N + 1) * NX;
+      for (int q = lane; q < (N + 1) * NX; q += LANES)
+        oh[q] = SINGLE ? ws[L.xs + q] : ws[L.w + (q / NX) * NZ + q % NX];
+    }
+    double xpred[NX];
+#pragma unroll
+    for (int i = 0; i < NX; ++i) xpred[i] = SINGLE ? ws[L.xs + NX + i] : ws[L.w + NZ + i];
     // plant step with the same discretisation: state = F(p, u0) (MS:273); Euler in SSv1:17-19
     {
       double xn[NX], q;
@@ -158,6 +183,11 @@ MPCV_D void closed_loop_problem(const Params& P, const Layout& L, WS ws, Grp<LAN
       for (int i = 0; i < NX; ++i) state[i] = xn[i];
       // `uprev` is never updated by the reference (Inverted_pendulum/...:64): replay on request
       if (Model::HAS_UPREV && io.warm_mode == MPCV_WARM_REFERENCE) state[NX - 1] = io.x_init[b * NX + NX - 1];
+      // next x0: the plant state, or the solver's own prediction x_1 (fixvar("x",0,var["x",1]),
+      // Trajectory_tracking.py:111-112)
+#pragma unroll
+      for (int i = 0; i < NX; ++i) xctrl[i] = (io.flags & MPCV_LOOP_X0_FROM_PREDICTION) ? xpred[i] : state[i];
+      if (Model::HAS_UPREV && io.warm_mode == MPCV_WARM_REFERENCE) xctrl[NX - 1] = io.x_init[b * NX + NX - 1];
     }
     if (lane == 0) {
 #pragma unroll

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cerrno>
+#include <cstdlib>
 #include <cstdint>
 #include <string>
 
@@ -28,6 +29,24 @@ struct mpcv_host_xfer {
   Arr out[7];    // x, f, g, lam_g, lam_x, status, iters    (dev -> host_dst)
 };
 
+// tuning overrides from the environment (they exist for the A/B measurements quoted in DESIGN.md and for the tests);
+// read ONCE, when a handle is created, never on the launch path.  -1 = the compiled-in default.
+struct mpcv_knobs {
+  int tail_cap = -1, tail_shift = -1, pipes = -1, warp_staged = -1;
+  long pipe_min = -1;
+  bool hostloop = false;
+};
+inline mpcv_knobs mpcv_knobs_from_env() {
+  mpcv_knobs k;
+  if (const char* env = getenv("MPCV_TAIL_BELOW")) k.tail_cap = atoi(env);
+  if (const char* env = getenv("MPCV_TAIL_SHIFT")) k.tail_shift = atoi(env);
+  if (const char* env = getenv("MPCV_PHASE_PIPES")) { const int v = atoi(env); if (v >= 1) k.pipes = v; }
+  if (const char* env = getenv("MPCV_PHASE_PIPE_MIN")) { const long v = atol(env); if (v >= 32) k.pipe_min = v; }
+  if (const char* env = getenv("MPCV_PHASE_HOSTLOOP")) k.hostloop = env[0] == '1';
+  if (const char* env = getenv("MPCV_WARP_STAGED")) k.warp_staged = atoi(env) & 3;
+  return k;
+}
+
 struct mpcv_handle {
   mpcv_spec spec;
   mpcv::Params P;
@@ -38,6 +57,10 @@ struct mpcv_handle {
   int device;
   int sm_count;
   size_t max_smem_optin;
+  size_t smem_per_sm;
+  mpcv_knobs knobs;
+  bool has_uprev = false;             // the model carries u_prev in its state (move blocking needs it)
+  cudaEvent_t last_done = nullptr;    // end of the handle's previous call: the next one waits for it on the device
   double* slab = nullptr;   // thread-layout workspace
   size_t slab_doubles = 0;
   long slab_stride = 0;
@@ -69,6 +92,7 @@ struct mpcv_phase_vtable {
   void (*release)(struct mpcv_phase_state*);
   int (*sweeps)(mpcv_handle*, cudaStream_t, int*, int*);
   int (*loop)(mpcv_handle*, const mpcv::LoopIO&, long, cudaStream_t);
+  int (*res_slots_per_sm)(const mpcv_handle*);   // problems an SM holds in the resident layout (0: does not fit)
 };
 const mpcv_phase_vtable* mpcv_phase_vtable_of(int model);
 #define MPCV_DECLARE_MODEL(id) \

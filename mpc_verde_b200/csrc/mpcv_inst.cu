@@ -206,6 +206,7 @@ __global__ void stage_derivs_kernel(const Params P, const double* z, const doubl
 template <class Model>
 static void fill_dims(mpcv_handle* h) {
   h->nx = Model::NX; h->nu = Model::NU; h->npg = Model::NPG; h->nps = Model::NPS;
+  h->has_uprev = Model::HAS_UPREV;
   const int N = h->spec.N;
   h->n_var = h->single ? Model::NU * N : Model::NX * (N + 1) + Model::NU * N;
   h->n_g = Model::NX * (N + 1);
@@ -255,7 +256,8 @@ static int warp_config(const mpcv_handle* h, int* wpb, size_t* smem) {
 template <class Model>
 static int launch_solve(mpcv_handle* h, const SolveIO& io, long B, cudaStream_t st) {
   if (B <= 0) return 0;
-  if (h->layout == MPCV_LAYOUT_PHASED && !h->single) return mpcv_phase_vtable_of(Model::MODEL_ID)->solve(h, io, B, st);
+  if ((h->layout == MPCV_LAYOUT_PHASED || h->layout == MPCV_LAYOUT_RESIDENT) && !h->single)
+    return mpcv_phase_vtable_of(Model::MODEL_ID)->solve(h, io, B, st);
   if (h->layout == MPCV_LAYOUT_WARP && !h->single) {
     int wpb; size_t smem;
     if (int rc = warp_config(h, &wpb, &smem)) return rc;
@@ -285,7 +287,8 @@ static int launch_loop(mpcv_handle* h, const LoopIO& io, long B, cudaStream_t st
   if (B <= 0) return 0;
   // phased layout: per-step prepare -> solve graph -> apply (mpcv_phase_inst.cu); otherwise the closed
   // loop runs as one kernel per call (warp or thread layout)
-  if (h->layout == MPCV_LAYOUT_PHASED && !h->single) return mpcv_phase_vtable_of(Model::MODEL_ID)->loop(h, io, B, st);
+  if ((h->layout == MPCV_LAYOUT_PHASED || h->layout == MPCV_LAYOUT_RESIDENT) && !h->single)
+    return mpcv_phase_vtable_of(Model::MODEL_ID)->loop(h, io, B, st);
   const bool warp = h->layout == MPCV_LAYOUT_WARP;
   if (warp && !h->single) {
     int wpb; size_t smem;

@@ -82,6 +82,7 @@ struct WsStrided {
 #endif
     return *p;
   }
+  MPCV_HD WsStrided view(int off) const { return WsStrided{base + (long)off * 32}; }
   MPCV_HD static WsStrided of(double* slab, int total, long b) {
     double* p = slab + (b >> 5) * ((long)total * 32) + (b & 31);
 #if defined(__CUDA_ARCH__)
@@ -94,6 +95,7 @@ struct WsStrided {
 struct WsDense {
   double* base;
   MPCV_HD double& operator[](int i) const { return base[i]; }
+  MPCV_HD WsDense view(int off) const { return WsDense{base + off}; }
 };
 template <class WS>
 struct WsView {
@@ -196,8 +198,13 @@ struct Ipm {
   // persistent scalar state of one solve (saved to / restored from ws[L.st..] between phase kernels)
   double df, mu, tau, f_curr;
   double theta_max, theta_min, delta_w_last;
-  double fil_phi[FILTER_MAX], fil_th[FILTER_MAX];
+  // the filter entries themselves stay in the workspace (state slots 16.., 24..): arrays indexed by a run-time
+  // nfil would live in local memory and be copied through it at every hand-over between phases
   int nfil, iter;
+  int acc_count;        // consecutive iterates within the acceptable tolerances
+  double f_last;        // objective at the previous convergence test
+  MPCV_D double& fil_phi(int q) const { return ws[L.st + 16 + q]; }
+  MPCV_D double& fil_th(int q) const { return ws[L.st + 24 + q]; }
   // search direction -> line search hand-over
   double ls_alpha_max, ls_theta, ls_gBD, ls_phi;
   // barrier log-sum of the current iterate = log-sum of the trial point accepted last (same slacks): reused by
@@ -210,7 +217,7 @@ struct Ipm {
              const BndEntry* tab = nullptr)
       : P(p), L(l), ws(w), g(grp), lbx(lb), ubx(ub), btab(tab), N(l.N), ps_base(l.par + NX + Model::NPG),
         df(1.0), mu(0.1), tau(0.99), f_curr(0), theta_max(-1.0), theta_min(-1.0), delta_w_last(0.0), nfil(0),
-        iter(0), ls_alpha_max(1.0), ls_theta(0.0), ls_gBD(0.0), ls_phi(0.0), lg_curr(0.0), lg_valid(false), lg_trial(0.0) {}
+        iter(0), acc_count(0), f_last(-1e50), ls_alpha_max(1.0), ls_theta(0.0), ls_gBD(0.0), ls_phi(0.0), lg_curr(0.0), lg_valid(false), lg_trial(0.0) {}
 
   // ---- state hand-over between phase kernels ---------------------------------------------------
   MPCV_D void save_state(int status) const {
@@ -221,7 +228,7 @@ struct Ipm {
     ws[o + 7] = (double)nfil; ws[o + 8] = (double)iter; ws[o + 9] = (double)status;
     ws[o + 10] = ls_alpha_max; ws[o + 11] = ls_theta; ws[o + 12] = ls_gBD; ws[o + 13] = ls_phi;
     ws[o + 35] = lg_curr; ws[o + 36] = lg_valid ? 1.0 : 0.0;
-    for (int q = 0; q < nfil; ++q) { ws[o + 16 + q] = fil_phi[q]; ws[o + 24 + q] = fil_th[q]; }
+    ws[o + 37] = (double)acc_count; ws[o + 38] = f_last;
   }
   MPCV_D int load_state() {
     const int o = L.st;
@@ -230,7 +237,7 @@ struct Ipm {
     nfil = (int)ws[o + 7]; iter = (int)ws[o + 8];
     ls_alpha_max = ws[o + 10]; ls_theta = ws[o + 11]; ls_gBD = ws[o + 12]; ls_phi = ws[o + 13];
     lg_curr = ws[o + 35]; lg_valid = ws[o + 36] != 0.0;
-    for (int q = 0; q < nfil; ++q) { fil_phi[q] = ws[o + 16 + q]; fil_th[q] = ws[o + 24 + q]; }
+    acc_count = (int)ws[o + 37]; f_last = ws[o + 38];
     return (int)ws[o + 9];
   }
 
@@ -729,7 +736,206 @@ struct Ipm {
     }
   }
 
-  MPCV_DN bool riccati_factor(double dw, bool identity) { return riccati_factor_t<false>(dw, identity, 0, -1); }
+  MPCV_DN bool riccati_factor(double dw, bool identity) { return riccati_factor_x<false>(dw, identity, 0, -1); }
+  // lane groups share the stage algebra (riccati_factor_lanes); a lone lane keeps everything in registers
+#if defined(MPCV_HOST_LANE_RICCATI)
+  static constexpr bool kLaneRiccati = true;      // tests/hostsim: replay the lane-parallel form with one lane
+#else
+  static constexpr bool kLaneRiccati = LANES > 1;
+#endif
+  template <bool FUSE>
+  MPCV_D bool riccati_factor_x(double dw, bool identity, int rmode, int coff) {
+    // (the scratch of the lane form must fit into the step buffers: always true but for toy horizons)
+    if (kLaneRiccati && (NX + 2 * NU) * (NX + 1) <= L.n + L.m) return riccati_factor_lanes<FUSE>(dw, identity, rmode, coff);
+    return riccati_factor_t<FUSE>(dw, identity, rmode, coff);
+  }
+
+  // ---- lane-parallel Riccati factorisation ---------------------------------------------------------------
+  // The backward recursion is sequential over the horizon, but inside a stage the NX columns of (P A, G, K),
+  // the vector part (P c + p, g, k_ff) and afterwards the entries of P_k and p_k are independent outputs: a
+  // stage is TWO short steps on the group's lanes with the operands exchanged through the workspace, instead
+  // of ~350 dependent instructions on lane 0.  Every output is accumulated by one lane with the expressions
+  // and the order of riccati_factor_t, so the two forms agree bit for bit (tests/hostsim replays this one with
+  // a single lane).  Scratch: the step buffers d, lam+ (contiguous, dead until the forward sweep writes them).
+  template <bool FUSE>
+  MPCV_D bool riccati_factor_lanes(double dw, bool identity, int rmode, int coff) {
+    // scratch in the step buffers: y = P A | P c + p  (NX x (NX+1)), z = G | g  (NU x (NX+1)), t = K | kff
+    constexpr int NC = NX + 1;
+    const WS sY = ws.view(L.d), sZ = ws.view(L.d + NX * NC), sT = ws.view(L.d + NX * NC + NU * NC);
+    // terminal stage: P_N = Sigma_N + dw (identity: I), p_N = r_N
+    {
+      const WS pn = ws.view(L.pp + N * NPP);
+      for (int i = g.lane; i < NPX + (FUSE ? NX : 0); i += LANES) {
+        if (i < NPX) {
+          int r = 0;
+#pragma unroll
+          for (int q = 1; q < NX; ++q) r += (i >= tri(q, 0)) ? 1 : 0;
+          const int c = i - tri(r, 0);
+          double v = 0.0;
+          if (r == c) {
+            double sg = 0.0, rr;
+            if (!identity) sigma_r(ix(N, r), &sg, &rr);
+            v = (identity ? 1.0 : 0.0) + sg + dw;
+          }
+          pn[i] = v;
+        } else {
+          pn[i] = rvar(rmode, ix(N, i - NPX));
+        }
+      }
+    }
+    g.sync();
+    int ok = 1;
+    for (int k = N - 1; k >= 0; --k) {
+      const WS ab = ws.view(L.ab + k * NAB), hw = ws.view(L.hw + k * NW), sgv = ws.view(L.sig + k * NZ);
+      const WS ric = ws.view(L.ric + k * NRIC), ppn = ws.view(L.pp + (k + 1) * NPP), ppk = ws.view(L.pp + k * NPP);
+      // ---- step A: item c < NX = column c of (P A, G, K); item NX = the vector part (P c + p, g, kff).  One
+      // instruction stream for both kinds (operands selected, not branched on): the lanes of a group stay together.
+      int okl = 1;
+      for (int it = g.lane; it < NX + (FUSE ? 1 : 0); it += LANES) {
+        const bool col = it < NX;
+        double Pm[NX * NX], B[NX * NU], PB[NX * NU], F[NU * NU], y[NX], z[NU], t[NU];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+#pragma unroll
+          for (int j = 0; j <= i; ++j) { const double v = ppn[tri(i, j)]; Pm[i * NX + j] = v; Pm[j * NX + i] = v; }
+        }
+#pragma unroll
+        for (int i = 0; i < NX * NU; ++i) B[i] = ab[NX * NX + i];
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+#pragma unroll
+          for (int j = 0; j < NU; ++j) {
+            double v = 0.0;
+#pragma unroll
+            for (int l = 0; l < NX; ++l) v += Pm[i * NX + l] * B[l * NU + j];
+            PB[i * NU + j] = v;
+          }
+        }
+        // F = Ruu + Sigma_u + dw + B'PB (lower)
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+#pragma unroll
+          for (int j = 0; j <= i; ++j) {
+            double v = identity ? (i == j ? 1.0 : 0.0) : hw[tri(NX + i, NX + j)];
+            if (!identity && i == j) v += sgv[NX + i] + dw;
+#pragma unroll
+            for (int l = 0; l < NX; ++l) v += B[l * NU + i] * PB[l * NU + j];
+            F[i * NU + j] = v;
+          }
+        }
+        bool fixed[NU];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) fixed[i] = bnd(iu(k, i)).fixed;
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+          if (fixed[i]) {
+#pragma unroll
+            for (int j = 0; j < NU; ++j) { if (j <= i) F[i * NU + j] = 0.0; else F[j * NU + i] = 0.0; }
+            F[i * NU + i] = 1.0;
+          }
+        }
+        // Cholesky of F in place (lower, reciprocal pivots on the diagonal)
+#pragma unroll
+        for (int j = 0; j < NU; ++j) {
+          double dj = F[j * NU + j];
+#pragma unroll
+          for (int l = 0; l < j; ++l) dj -= F[j * NU + l] * F[j * NU + l];
+          if (!(dj > 0.0) || !(dj < INFINITY)) { okl = 0; dj = 1.0; }
+          dj = rsqrt_(dj);
+          F[j * NU + j] = dj;
+#pragma unroll
+          for (int i = j + 1; i < NU; ++i) {
+            double v = F[i * NU + j];
+#pragma unroll
+            for (int l = 0; l < j; ++l) v -= F[i * NU + l] * F[j * NU + l];
+            F[i * NU + j] = v * dj;
+          }
+        }
+        // y = P a + y0:  column c: a = A[:, c], y0 = 0  (P A);  vector item: a = c_{k+1}, y0 = p_{k+1}  (P c + p)
+        const WS av = col ? ws.view(L.ab + k * NAB + it) : ws.view(coff >= 0 ? coff + (k + 1) * NX : L.ab + k * NAB);
+        const int astr = col ? NX : 1;
+        const bool azero = !col && coff < 0;
+        double a[NX];
+#pragma unroll
+        for (int l = 0; l < NX; ++l) { const double v = av[l * astr]; a[l] = azero ? 0.0 : v; }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+          double v = col ? 0.0 : ppn[NPX + i];
+#pragma unroll
+          for (int l = 0; l < NX; ++l) v += Pm[i * NX + l] * a[l];
+          y[i] = v;
+        }
+        // z = z0 + B' y:  column: z0 = S_ux[:, c]  (G);  vector: z0 = r_u  (g);  fixed controls drop out
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+          double v;
+          if (col) v = identity ? 0.0 : hw[tri(NX + i, 0) + it];
+          else v = rvar(rmode, iu(k, i));
+#pragma unroll
+          for (int l = 0; l < NX; ++l) v += B[l * NU + i] * y[l];
+          z[i] = fixed[i] ? 0.0 : v;
+        }
+        // t = -F^{-1} z  (K[:, c] | kff)
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+          double v = -z[i];
+#pragma unroll
+          for (int l = 0; l < i; ++l) v -= F[i * NU + l] * t[l];
+          t[i] = v * F[i * NU + i];
+        }
+#pragma unroll
+        for (int i = NU - 1; i >= 0; --i) {
+          double v = t[i];
+#pragma unroll
+          for (int l = i + 1; l < NU; ++l) v -= F[l * NU + i] * t[l];
+          t[i] = v * F[i * NU + i];
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) sY[i * NC + it] = y[i];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+          sZ[i * NC + it] = z[i];
+          sT[i * NC + it] = t[i];
+          ric[col ? i * NX + it : NU * NX + i] = t[i];
+        }
+        if (it == 0) {
+#pragma unroll
+          for (int i = 0; i < NU; ++i) {
+#pragma unroll
+            for (int j = 0; j <= i; ++j) ric[NU * NX + NU + tri(i, j)] = F[i * NU + j];
+          }
+        }
+      }
+      ok = (LANES > 1) ? (g.min(okl ? 1.0 : 0.0) > 0.0 ? 1 : 0) : okl;
+      g.sync();
+      if (!ok) break;
+      // ---- step B: the entries of P_k = Qxx + A'PA + G'K and of p_k = r_x + A' Pd + K' g ----
+      for (int it = g.lane; it < NPX + (FUSE ? NX : 0); it += LANES) {
+        const bool mat = it < NPX;
+        int i = 0;
+#pragma unroll
+        for (int q = 1; q < NX; ++q) i += (it >= tri(q, 0)) ? 1 : 0;
+        const int j = mat ? it - tri(i, 0) : NX;      // column of (y, z, t): a matrix column or the vector part
+        if (!mat) i = it - NPX;
+        double v;
+        if (mat) {
+          v = identity ? (i == j ? 1.0 : 0.0) : hw[it];
+          if (!identity && i == j) v += sgv[i] + dw;
+        } else {
+          v = rvar(rmode, ix(k, i));
+        }
+#pragma unroll
+        for (int l = 0; l < NX; ++l) v += ab[l * NX + i] * sY[l * NC + j];
+        // G'K for the matrix entries, K'g for the vector ones: (row l of z | t) x (row l of t | z)
+#pragma unroll
+        for (int l = 0; l < NU; ++l) v += mat ? sZ[l * NC + i] * sT[l * NC + j] : sT[l * NC + i] * sZ[l * NC + NX];
+        ppk[mat ? it : NPX + i] = v;
+      }
+      g.sync();
+    }
+    return ok != 0;
+  }
+
   // inertia probe: the factorisation without any store (only its verdict matters)
   MPCV_D bool riccati_probe(double dw) { return riccati_factor_t<false, false>(dw, false, 0, -1); }
   // FUSE: the backward VECTOR recursion of riccati_solve(rmode, coff) runs inside the factorisation loop,
@@ -1355,6 +1561,8 @@ struct Ipm {
     theta_max = theta_min = -1.0;
     delta_w_last = 0.0;
     iter = 0;
+    acc_count = 0;
+    f_last = -1e50;            // IPOPT: last_obj_val_ starts at -1e50
     lg_valid = false;
   }
 
@@ -1400,6 +1608,16 @@ struct Ipm {
       const double dual_u = e.dual * e.sd / df, compl_u = compl_err(e, 0.0) * e.sc / df;
       if (E0 <= P.tol && dual_u <= P.dual_inf_tol && e.prim <= P.constr_viol_tol && compl_u <= P.compl_inf_tol)
         return MPCV_SOLVE_SUCCEEDED;
+      // acceptable level (IpOptErrorConvCheck::CurrentIsAcceptable): acceptable_iter consecutive iterates within
+      // acceptable_tol (and IPOPT's fixed acceptable_dual_inf / constr_viol / compl_inf tolerances 1e10 / 1e-2 / 1e-2)
+      // whose objective moved by no more than acceptable_obj_change_tol.  The scripts set acceptable_tol = tol
+      // (single_shooting_v1.py:121-129), so the regular test fires first there.
+      const bool acc = P.acceptable_iter > 0 && E0 <= P.acceptable_tol && dual_u <= 1e10 && e.prim <= 1e-2 &&
+                       compl_u <= 1e-2 &&
+                       fabs(f_curr - f_last) / fmax(1.0, fabs(f_curr)) <= P.acceptable_obj_change_tol;
+      f_last = f_curr;
+      if (acc) { if (++acc_count >= P.acceptable_iter) return MPCV_SOLVED_TO_ACCEPTABLE_LEVEL; }
+      else acc_count = 0;
     }
     if (iter >= P.max_iter) return MPCV_MAXIMUM_ITERATIONS_EXCEEDED;
     if (!(E0 < INFINITY)) return MPCV_INVALID_NUMBER_DETECTED;
@@ -1419,9 +1637,14 @@ struct Ipm {
   // of the current iterate.  direction_first() tries delta_w = 0; direction_retry() walks IPOPT's
   // delta_w schedule after a failed first attempt (the phase pipeline runs the retries as a separate,
   // compacted launch so that warps without wrong inertia do not idle through them).
+  // factorisation of the Newton system with the backward vector recursion fused in (multiple shooting)
+  MPCV_D bool factor_dir(double dw) {
+    if (SINGLE) return condensed_factor(dw);
+    return riccati_factor_x<true>(dw, false, 0, L.c);
+  }
   MPCV_DN bool direction_first() {
     prepare_barrier();
-    const bool ok = SINGLE ? condensed_factor(0.0) : riccati_factor(0.0, false);
+    const bool ok = factor_dir(0.0);
     if (ok) direction_finish(0.0);
     return ok;
   }
@@ -1438,7 +1661,7 @@ struct Ipm {
     while (!ok) {
       dw = next_delta_w(dw);
       if (dw > 1e20) break;
-      ok = SINGLE ? condensed_factor(dw) : riccati_factor(dw, false);
+      ok = factor_dir(dw);
     }
     if (!ok) return MPCV_ERROR_IN_STEP_COMPUTATION;
     direction_finish(dw);
@@ -1446,7 +1669,7 @@ struct Ipm {
   }
   MPCV_D void direction_finish(double dw) {
     if (dw > 0.0) delta_w_last = dw;
-    if (SINGLE) condensed_solve(); else riccati_solve(0, L.c);
+    if (SINGLE) condensed_solve(); else riccati_forward(L.c);
     direction_post();
   }
   // maximal primal step (fraction to the boundary) and the merit-function terms of the current iterate
@@ -1503,8 +1726,10 @@ struct Ipm {
       acc = compare_le(theta_t, (1.0 - 1e-5) * theta, theta) || compare_le(phi_t - phi, -1e-8 * theta, phi);
     }
     if (!acc) return false;
-    for (int q = 0; q < nfil; ++q)
-      if (!(compare_le(phi_t, fil_phi[q], fil_phi[q]) || compare_le(theta_t, fil_th[q], fil_th[q]))) return false;
+    for (int q = 0; q < nfil; ++q) {
+      const double fp = fil_phi(q), ft = fil_th(q);
+      if (!(compare_le(phi_t, fp, fp) || compare_le(theta_t, ft, ft))) return false;
+    }
     return true;
   }
   // filter augmentation, dual step length and the update of (w, z, lam) for an accepted step
@@ -1517,12 +1742,14 @@ struct Ipm {
   MPCV_D void ls_filter_augment(double alpha_test, double phi_acc, const LsPow& pw) {
     const double theta = ls_theta, phi = ls_phi;
     if (!ls_is_ftype(alpha_test, pw) || !ls_armijo(alpha_test, phi_acc)) {
+      // (one lane writes; the step that follows synchronises the group before the filter is read again)
       if (nfil < FILTER_MAX) {
-        fil_phi[nfil] = phi - 1e-8 * theta; fil_th[nfil] = (1.0 - 1e-5) * theta; ++nfil;
-      } else {
+        if (g.lane == 0) { fil_phi(nfil) = phi - 1e-8 * theta; fil_th(nfil) = (1.0 - 1e-5) * theta; }
+        ++nfil;
+      } else if (g.lane == 0) {
         // filter full: drop the oldest entry
-        for (int q = 1; q < FILTER_MAX; ++q) { fil_phi[q - 1] = fil_phi[q]; fil_th[q - 1] = fil_th[q]; }
-        fil_phi[FILTER_MAX - 1] = phi - 1e-8 * theta; fil_th[FILTER_MAX - 1] = (1.0 - 1e-5) * theta;
+        for (int q = 1; q < FILTER_MAX; ++q) { fil_phi(q - 1) = fil_phi(q); fil_th(q - 1) = fil_th(q); }
+        fil_phi(FILTER_MAX - 1) = phi - 1e-8 * theta; fil_th(FILTER_MAX - 1) = (1.0 - 1e-5) * theta;
       }
     }
   }

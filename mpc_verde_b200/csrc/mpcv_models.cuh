@@ -44,7 +44,8 @@ struct Params {
   // IPOPT options
   double tol, mu_init, bound_push, bound_frac, bound_relax, scal_max_grad;
   double dual_inf_tol, constr_viol_tol, compl_inf_tol;
-  int max_iter, max_soc;
+  double acceptable_tol, acceptable_obj_change_tol;
+  int max_iter, max_soc, acceptable_iter;
 };
 
 MPCV_HD void sincos_(double a, double* s, double* c) {

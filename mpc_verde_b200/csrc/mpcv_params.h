@@ -27,6 +27,9 @@ inline Params params_from_spec(const mpcv_spec& s) {
   P.dual_inf_tol = s.dual_inf_tol > 0 ? s.dual_inf_tol : 1.0;
   P.constr_viol_tol = s.constr_viol_tol > 0 ? s.constr_viol_tol : 1e-4;
   P.compl_inf_tol = s.compl_inf_tol > 0 ? s.compl_inf_tol : 1e-4;
+  P.acceptable_tol = s.acceptable_tol > 0 ? s.acceptable_tol : 1e-6;
+  P.acceptable_iter = s.acceptable_iter != 0 ? s.acceptable_iter : 15;
+  P.acceptable_obj_change_tol = s.acceptable_obj_change_tol > 0 ? s.acceptable_obj_change_tol : 1e20;
   return P;
 }
 

@@ -63,6 +63,7 @@ struct PhaseCtrl {
   int slots;      // workspace slots in use since the last repack (the lists hold slot indices)
   int repacks;    // repacks of this call
   int tail_below; // at most this many active problems: leave the sweeps, finish in ph_tail_kernel
+  int row0;       // first queue entry of this pipe's share (entry e of the call <-> I/O row index[e], or e)
 };
 constexpr int kRepackMin = 512;     // do not bother to repack fewer survivors than this
 #ifndef MPCV_REPACK_SPLIT
@@ -88,23 +89,33 @@ struct Phase {
   using Ipm1 = Ipm<Model, false, 1, WS>;
   static constexpr int NX = Model::NX, NH = Model::NX + Model::NPG;
 
+  // the solver object of one problem: bounds shared by the batch (precomputed table) or the problem's own rows
+  template <class I, class G>
+  MPCV_HD static I make_ipm(const Params& P, const Layout& L, WS ws, G g, const SolveIO& io, const BndEntry* tab) {
+    if (io.bstride) {
+      const long b = (long)ws[L.st + 15];
+      return I(P, L, ws, g, io.lbx + b * io.bstride, io.ubx + b * io.bstride, nullptr);
+    }
+    return I(P, L, ws, g, io.lbx, io.ubx, tab);
+  }
+
   // load x0 / p, push into the interior, z0, lam0; state := running            (thread per problem)
   MPCV_HD static void init_body(const Params& P, const Layout& L, WS ws, const SolveIO& io, long b,
                                 const BndEntry* tab, long long t0) {
     const int np = NH + L.N * Model::NPS;
     for (int i = 0; i < L.n; ++i) ws[L.w + i] = io.x0 ? io.x0[b * L.n + i] : 0.0;
     for (int i = 0; i < np; ++i) ws[L.par + i] = io.p[b * np + i];
-    Ipm1 ipm(P, L, ws, Grp<1>(0), io.lbx, io.ubx, tab);
+    ws[L.st + 15] = (double)b;          // the problem's row in the caller's batch (slots move on repack)
+    Ipm1 ipm = make_ipm<Ipm1>(P, L, ws, Grp<1>(0), io, tab);
     ipm.start();
     ipm.save_state(kRunning);
     ws[L.st + 14] = long_as_double(t0);
-    ws[L.st + 15] = (double)b;          // the problem's index in the caller's batch (slots move on repack)
   }
 
   // derivative sweep, one shooting interval                                   (thread per interval)
   MPCV_HD static void der_body(const Params& P, const Layout& L, WS ws, const SolveIO& io, int k, bool want_hess,
                                const BndEntry* tab) {
-    Ipm1 ipm(P, L, ws, Grp<1>(0), io.lbx, io.ubx, tab);
+    Ipm1 ipm = make_ipm<Ipm1>(P, L, ws, Grp<1>(0), io, tab);
     ipm.df = ws[L.st + 0];
     ws[L.qs + k] = ipm.der_stage(k, want_hess);
     if (k == 0) ipm.der_terminal();
@@ -112,7 +123,7 @@ struct Phase {
 
   // objective scaling + least-squares multipliers (after the first derivative sweep at df = 1)
   MPCV_HD static void init2_body(const Params& P, const Layout& L, WS ws, const SolveIO& io, const BndEntry* tab) {
-    Ipm1 ipm(P, L, ws, Grp<1>(0), io.lbx, io.ubx, tab);
+    Ipm1 ipm = make_ipm<Ipm1>(P, L, ws, Grp<1>(0), io, tab);
     ipm.load_state();
     ipm.f_curr = ipm.sum_stage_costs();
     ipm.init_scaling_and_multipliers();
@@ -123,7 +134,7 @@ struct Phase {
   // active; otherwise it is finished and its solution has been exported.        (LANES lanes per problem)
   MPCV_HD static bool pre_body(const Params& P, const Layout& L, WS ws, const SolveIO& io, long b,
                                const BndEntry* tab, Grp<LANES> g, long long now) {
-    IpmT ipm(P, L, ws, g, io.lbx, io.ubx, tab);
+    IpmT ipm = make_ipm<IpmT>(P, L, ws, g, io, tab);
     int st = ipm.load_state();
     if (st != kRunning) return false;                 // failed earlier in this solve: already exported
     ipm.f_curr = ipm.sum_stage_costs();
@@ -140,7 +151,7 @@ struct Phase {
   // Riccati factorisation with delta_w = 0 and, when the inertia is right, the vector recursions.
   // Returns false when the delta_w schedule has to take over.                    (thread per problem)
   MPCV_HD static bool factor_body(const Params& P, const Layout& L, WS ws, const SolveIO& io, const BndEntry* tab) {
-    Ipm1 ipm(P, L, ws, Grp<1>(0), io.lbx, io.ubx, tab);
+    Ipm1 ipm = make_ipm<Ipm1>(P, L, ws, Grp<1>(0), io, tab);
     if (!ipm.template riccati_factor_t<true>(0.0, false, 0, L.c)) return false;
     ipm.riccati_forward(L.c);
     return true;
@@ -157,7 +168,7 @@ struct Phase {
   }
   MPCV_HD static bool probe_body(const Params& P, const Layout& L, WS ws, const SolveIO& io, const BndEntry* tab,
                                  int attempt, double* dw_out) {
-    Ipm1 ipm(P, L, ws, Grp<1>(0), io.lbx, io.ubx, tab);
+    Ipm1 ipm = make_ipm<Ipm1>(P, L, ws, Grp<1>(0), io, tab);
     ipm.delta_w_last = ws[L.st + 6];
     const double dw = probe_dw(ipm, attempt);
     *dw_out = dw;
@@ -169,7 +180,7 @@ struct Phase {
   // where the store-free probe succeeded, the problem goes to the sequential walk with hint = -dw.
   MPCV_HD static void apply_body(const Params& P, const Layout& L, WS ws, const SolveIO& io, const BndEntry* tab,
                                  double dw) {
-    Ipm1 ipm(P, L, ws, Grp<1>(0), io.lbx, io.ubx, tab);
+    Ipm1 ipm = make_ipm<Ipm1>(P, L, ws, Grp<1>(0), io, tab);
     if (!ipm.template riccati_factor_t<true>(dw, false, 0, L.c)) { ws[L.st + kSlotDwHint] = -dw; return; }
     ws[L.st + 6] = dw;
     ws[L.st + kSlotDwHint] = dw;          // > 0: done, ph_retry_kernel skips it
@@ -179,7 +190,7 @@ struct Phase {
   // sequentially, then the vector sweeps                                          (thread per problem)
   MPCV_HD static void retry_body(const Params& P, const Layout& L, WS ws, const SolveIO& io, long b,
                                  const BndEntry* tab, long long now) {
-    Ipm1 ipm(P, L, ws, Grp<1>(0), io.lbx, io.ubx, tab);
+    Ipm1 ipm = make_ipm<Ipm1>(P, L, ws, Grp<1>(0), io, tab);
     ipm.delta_w_last = ws[L.st + 6];
     const double hint = ws[L.st + kSlotDwHint];
     if (hint > 0.0) return;               // settled by the probe's winning lane
@@ -204,7 +215,7 @@ struct Phase {
   // fraction-to-the-boundary step and merit-function terms                      (LANES lanes per problem)
   MPCV_HD static void post_body(const Params& P, const Layout& L, WS ws, const SolveIO& io, const BndEntry* tab,
                                 Grp<LANES> g) {
-    IpmT ipm(P, L, ws, g, io.lbx, io.ubx, tab);
+    IpmT ipm = make_ipm<IpmT>(P, L, ws, g, io, tab);
     ipm.load_state();
     ipm.direction_post();
     ipm.save_state(kRunning);
@@ -213,7 +224,7 @@ struct Phase {
   // first line-search trial point, one shooting interval                         (thread per interval)
   MPCV_HD static void trial_body(const Params& P, const Layout& L, WS ws, const SolveIO& io, int k,
                                  const BndEntry* tab) {
-    Ipm1 ipm(P, L, ws, Grp<1>(0), io.lbx, io.ubx, tab);
+    Ipm1 ipm = make_ipm<Ipm1>(P, L, ws, Grp<1>(0), io, tab);
     ipm.trial_stage(k, ws[L.st + 10], L.d);
   }
 
@@ -221,7 +232,7 @@ struct Phase {
   // the slow path (nothing has been modified then).                              (LANES lanes per problem)
   MPCV_HD static bool accept_body(const Params& P, const Layout& L, WS ws, const SolveIO& io, const BndEntry* tab,
                                   Grp<LANES> g) {
-    IpmT ipm(P, L, ws, g, io.lbx, io.ubx, tab);
+    IpmT ipm = make_ipm<IpmT>(P, L, ws, g, io, tab);
     ipm.load_state();
     if (!ipm.line_search_first()) return false;
     ipm.save_state(kRunning);
@@ -231,7 +242,7 @@ struct Phase {
   // slow path: backtracking and second-order correction                          (LANES lanes per problem)
   MPCV_HD static void slow_body(const Params& P, const Layout& L, WS ws, const SolveIO& io, long b,
                                 const BndEntry* tab, Grp<LANES> g, long long now) {
-    IpmT ipm(P, L, ws, g, io.lbx, io.ubx, tab);
+    IpmT ipm = make_ipm<IpmT>(P, L, ws, g, io, tab);
     ipm.load_state();
     const int st = ipm.line_search(true);
     if (st != 0) { finish(ipm, st, io, b, now); return; }
@@ -243,7 +254,7 @@ struct Phase {
   // Precondition: a derivative sweep at the current iterate has been done (as at the top of every sweep).
   MPCV_HD static void tail_body(const Params& P, const Layout& L, WS ws, const SolveIO& io, long b,
                                 const BndEntry* tab, Grp<LANES> g, long long now) {
-    IpmT ipm(P, L, ws, g, io.lbx, io.ubx, tab);
+    IpmT ipm = make_ipm<IpmT>(P, L, ws, g, io, tab);
     int st = ipm.load_state();
     if (st != kRunning) return;
     ipm.f_curr = ipm.sum_stage_costs();
@@ -347,10 +358,11 @@ __global__ void __launch_bounds__(kPhaseThreads) ph_init_kernel(const __grid_con
   double* const slab = a.slab[a.ctrl->cur];
   const SolveIO io = *a.io;
   const BndEntry* tab = ph_bounds_table<Model>(a.P, a.L, io);
-  const long B = a.ctrl->B;
+  const long B = a.ctrl->B, row0 = a.ctrl->row0;
   for (long b = (long)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (long)gridDim.x * blockDim.x) {
     a.act[0][b] = (int)b;
-    Phase<Model, WsStrided>::init_body(a.P, a.L, WsStrided::of(slab, a.L.total, b), io, b, tab,
+    const long row = io.index ? (long)io.index[row0 + b] : row0 + b;
+    Phase<Model, WsStrided>::init_body(a.P, a.L, WsStrided::of(slab, a.L.total, b), io, row, tab,
                                        io.ns ? ph_globaltimer() : 0);
   }
 }
@@ -623,7 +635,7 @@ __device__ __forceinline__ void ph_accept_run(const PhaseArgs& a, double* slab, 
     const int b = act ? a.act[out][e] : 0;
     const WsStrided ws = WsStrided::of(slab, a.L.total, b);
     act = act && Phase<Model, WsStrided>::running(a.L, ws);
-    IpmT ipm(a.P, a.L, ws, g, io.lbx, io.ubx, tab);
+    IpmT ipm = Phase<Model, WsStrided, LANES>::template make_ipm<IpmT>(a.P, a.L, ws, g, io, tab);
     typename IpmT::LsFirst r;
     r.ok = false;
     if (act) {
@@ -665,6 +677,7 @@ __global__ void __launch_bounds__(kWarpPhaseThreads, MPCV_GROUP_MINB) ph_accept_
 struct WsShared {
   double* row;
   __device__ __forceinline__ double& operator[](int i) const { return row[i]; }
+  __device__ __forceinline__ WsShared view(int off) const { return WsShared{row + off}; }
 };
 __device__ __forceinline__ void ph_cp_async8(double* dst_smem, const double* src) {
   const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
@@ -768,14 +781,6 @@ __global__ void __launch_bounds__(kWarpPhaseThreads, MPCV_TAIL_MINB) ph_tail_ker
 #ifndef MPCV_TAIL_SHIFT
 #define MPCV_TAIL_SHIFT 4
 #endif
-inline int ph_tail_below(int B) {
-  int cap = kTailBelow, shift = MPCV_TAIL_SHIFT;
-  if (const char* env = getenv("MPCV_TAIL_BELOW")) cap = atoi(env);       // tuning overrides
-  if (const char* env = getenv("MPCV_TAIL_SHIFT")) shift = atoi(env);
-  const int t = B >> shift;
-  return t < 32 ? 32 : (t > cap ? cap : t);
-}
-
 // end of an iteration sweep: swap the lists and tell the WHILE node whether anyone is left
 static __global__ void ph_flip_kernel(PhaseCtrl* ctrl, cudaGraphConditionalHandle handle, int use_handle) {
   const int in = ctrl->sweep & 1, out = in ^ 1;
@@ -793,10 +798,22 @@ static __global__ void ph_flip_kernel(PhaseCtrl* ctrl, cudaGraphConditionalHandl
   if (use_handle) cudaGraphSetConditional(handle, ctrl->n_act[out] > ctrl->tail_below ? 1u : 0u);
 }
 
-static __global__ void ph_begin_kernel(PhaseCtrl* ctrl, SolveIO* dst, const SolveIO io, int B, int tail_below) {
+// start of a solve on pipe j of K: the pipe's share of the queue (contiguous, a multiple of 32 entries so that every
+// share starts on a slab block).  The number of entries is the host's B or, for closed loops over the live
+// scenarios, a device counter.
+__host__ __device__ inline long ph_share_of(long cnt, int K) { return ((cnt + K - 1) / K + 31) / 32 * 32; }
+static __global__ void ph_begin_kernel(PhaseCtrl* ctrl, SolveIO* dst, const SolveIO io, long B_host, int j, int K,
+                                       int tail_cap, int tail_shift) {
   *dst = io;
+  const long cnt = io.count ? (long)*io.count : B_host;
+  const long share = ph_share_of(cnt, K), e0 = (long)j * share;
+  long nb = cnt - e0;
+  nb = nb < 0 ? 0 : (nb > share ? share : nb);
+  const int B = (int)nb;
+  const int t = B >> tail_shift;
+  ctrl->row0 = (int)e0;
   ctrl->B = B;
-  ctrl->tail_below = tail_below;
+  ctrl->tail_below = t < 32 ? 32 : (t > tail_cap ? tail_cap : t);
   ctrl->n_act[0] = B; ctrl->n_act[1] = 0; ctrl->sweep = 0; ctrl->sweeps_total = 0;
   ctrl->n_retry = 0; ctrl->n_slow = 0;
   ctrl->cur = 0; ctrl->slots = B; ctrl->repacks = 0;
@@ -818,6 +835,10 @@ struct LoopBufs {
   int* steps;       // [B]
   int* iters_total; // [B]
   int* worst;       // [B]
+  double* xctrl;    // [B, nx]  the controller's x0 (the plant state unless MPCV_LOOP_X0_FROM_PREDICTION)
+  int* index;       // [B]      live scenarios of the current step (queue of the solve)
+  int* count;       // [1]      their number
+  long long* t0;    // [1]      device-timer stamp of the current step's start
 };
 
 template <class Model>
@@ -826,7 +847,8 @@ __global__ void lp_begin_kernel(const Layout L, const LoopIO io, const LoopBufs 
   const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   double* os = io.out_states + b * (long)(io.n_steps + 1) * NX;
-  for (int i = 0; i < NX; ++i) { const double v = io.x_init[b * NX + i]; lb.state[b * NX + i] = v; os[i] = v; }
+  for (int i = 0; i < NX; ++i) { const double v = io.x_init[b * NX + i]; lb.state[b * NX + i] = v; lb.xctrl[b * NX + i] = v; os[i] = v; }
+  if (b == 0) *lb.count = 0;
   // first guess: X_k = state, U = 0 (repmat(state_init) of MS:213); the scripts' own w0 = 0 in reference mode
   double* g = lb.x0 + b * L.n;
   for (int i = 0; i < L.n; ++i) g[i] = 0.0;
@@ -840,34 +862,51 @@ template <class Model>
 __global__ void lp_prepare_kernel(const Layout L, const LoopIO io, const LoopBufs lb, long B, int t) {
   constexpr int NX = Model::NX, NU = Model::NU, NZ = NX + NU, NPG = Model::NPG, NPS = Model::NPS;
   const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  const int np = NX + NPG + L.N * NPS;
-  double* pr = lb.p + b * np;
-  const double* st = lb.state + b * NX;
-  for (int i = 0; i < NPG; ++i) pr[NX + i] = io.pglob[b * NPG + i];
-  if (lb.active[b] && io.stop_radius > 0.0 && NPG >= NX) {
-    double d2 = 0.0;
-    for (int i = 0; i < NX; ++i) { const double e = st[i] - pr[NX + i]; d2 += e * e; }
-    if (!(sqrt(d2) > io.stop_radius)) lb.active[b] = 0;      // while norm_2(state-target) > 1e-1 (MS:226)
+  if (b == 0 && io.out_step_ns) *lb.t0 = ph_globaltimer();
+  bool live = false;
+  if (b < B) {
+    const int np = NX + NPG + L.N * NPS;
+    double* pr = lb.p + b * np;
+    const double* st = lb.state + b * NX;
+    // model parameters: constant, or those of step t (LTV: Trjectory_tracking_le_LTV.py:126-143)
+    const double* pg = io.pglob_traj ? io.pglob_traj + (b * (long)io.n_steps + t) * NPG : io.pglob + b * NPG;
+    for (int i = 0; i < NPG; ++i) pr[NX + i] = pg[i];
+    live = lb.active[b] != 0;
+    if (live && io.stop_radius > 0.0 && NPG >= NX) {
+      double d2 = 0.0;
+      for (int i = 0; i < NX; ++i) { const double e = st[i] - pr[NX + i]; d2 += e * e; }
+      if (!(sqrt(d2) > io.stop_radius)) { lb.active[b] = 0; live = false; }   // while norm_2(state-target) > 1e-1 (MS:226)
+    }
+    if (live) {
+      const double* xc = lb.xctrl + b * NX;
+      for (int i = 0; i < NX; ++i) pr[i] = xc[i];
+      if (NPS > 0) {
+        // horizon window p[t..t+N) of this scenario's reference trajectory, or the step's own window table
+        const double* src = (io.flags & MPCV_LOOP_PTRAJ_WINDOWS)
+                                ? io.ptraj + (b * (long)io.n_steps + t) * (long)L.N * NPS
+                                : io.ptraj + (b * (long)(io.n_steps + L.N) + t) * NPS;
+        for (int i = 0; i < L.N * NPS; ++i) pr[NX + NPG + i] = src[i];
+      }
+      if (io.warm_mode == MPCV_WARM_COLD) {
+        double* g = lb.x0 + b * L.n;
+        for (int i = 0; i < L.n; ++i) g[i] = 0.0;
+        for (int k = 0; k <= L.N; ++k)
+          for (int i = 0; i < NX; ++i) g[k * NZ + i] = xc[i];
+      }
+    }
   }
-  for (int i = 0; i < NX; ++i) pr[i] = st[i];
-  if (NPS > 0) {
-    // horizon window p[t..t+N) of this scenario's reference trajectory
-    const double* src = io.ptraj + (b * (long)(io.n_steps + L.N) + t) * NPS;
-    for (int i = 0; i < L.N * NPS; ++i) pr[NX + NPG + i] = src[i];
-  }
-  if (io.warm_mode == MPCV_WARM_COLD) {
-    double* g = lb.x0 + b * L.n;
-    for (int i = 0; i < L.n; ++i) g[i] = 0.0;
-    for (int k = 0; k <= L.N; ++k)
-      for (int i = 0; i < NX; ++i) g[k * NZ + i] = st[i];
-  }
+  // the queue of this step's solve: scenarios whose loop is still running (finished ones are not solved again)
+  ph_append(live, (int)b, lb.index, lb.count);
 }
 
 template <class Model>
 __global__ void lp_apply_kernel(const Params P, const Layout L, const LoopIO io, const LoopBufs lb, long B, int t) {
   constexpr int NX = Model::NX, NU = Model::NU, NZ = NX + NU, NPG = Model::NPG, NPS = Model::NPS;
   const long b = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b == 0) {
+    if (io.out_step_ns) io.out_step_ns[t] = ph_globaltimer() - *lb.t0;   // `times` of single_shooting_v1.py:209-212
+    *lb.count = 0;                                                        // the next step builds its own queue
+  }
   if (b >= B || !lb.active[b]) return;
   const int N = L.N, np = NX + NPG + N * NPS;
   const double* pr = lb.p + b * np;
@@ -885,6 +924,17 @@ __global__ void lp_apply_kernel(const Params P, const Layout L, const LoopIO io,
   double* oc = io.out_controls + b * (long)io.n_steps * NU;
   for (int i = 0; i < NU; ++i) oc[t * NU + i] = u0[i];
   for (int i = 0; i < NX; ++i) { os[(t + 1) * NX + i] = xn[i]; st[i] = xn[i]; }
+  // the next solve starts from the plant state, or from the solver's own prediction x_1
+  // (solver.fixvar("x",0,solver.var["x",1]), Trajectory_tracking.py:111-112)
+  double* xc = lb.xctrl + b * NX;
+  for (int i = 0; i < NX; ++i) xc[i] = (io.flags & MPCV_LOOP_X0_FROM_PREDICTION) ? x[NZ + i] : xn[i];
+  if (Model::HAS_UPREV && io.warm_mode == MPCV_WARM_REFERENCE) xc[NX - 1] = io.x_init[b * NX + NX - 1];
+  if (io.out_horizons) {
+    // predicted horizon of this solve (cat_states of single_shooting_v1.py:185-188)
+    double* oh = io.out_horizons + (b * (long)io.n_steps + t) * (long)(N + 1) * NX;
+    for (int k = 0; k <= N; ++k)
+      for (int i = 0; i < NX; ++i) oh[k * NX + i] = x[k * NZ + i];
+  }
   lb.steps[b] += 1;
   lb.iters_total[b] += lb.iters[b];
   if (lb.status[b] != 0 && lb.worst[b] == 0) lb.worst[b] = lb.status[b];

@@ -6,6 +6,7 @@
 #define MPCV_INLINE_PHASES 1
 #include "mpcv_host.h"
 #include "mpcv_phase.cuh"
+#include "mpcv_resident.cuh"
 
 using namespace mpcv;
 
@@ -53,13 +54,15 @@ struct mpcv_phase_state {
   size_t slab2_doubles = 0;
   long cap = 0;                     // problems PER PIPE the lists / grids are sized for
   bool graph_failed = false;
+  ResCtrl* res_ctrl = nullptr;      // problem queue of the resident layout
+  bool res_attr_set = false;
   double* graph_slab = nullptr;     // the graphs bake these in: rebuild when they change
   long graph_stride = 0;
 };
 
 static void loop_free(mpcv_phase_state* s) {
   void* ptrs[] = {s->lb.x0, s->lb.p, s->lb.x, s->lb.f, s->lb.state, s->lb.status, s->lb.iters, s->lb.active,
-                  s->lb.steps, s->lb.iters_total, s->lb.worst};
+                  s->lb.steps, s->lb.iters_total, s->lb.worst, s->lb.xctrl, s->lb.index, s->lb.count, s->lb.t0};
   for (void* q : ptrs) if (q) cudaFree(q);
   s->lb = LoopBufs{};
   s->lb_cap = 0;
@@ -81,6 +84,7 @@ static void phase_free(mpcv_phase_state* s) {
   }
   if (s->fork) cudaEventDestroy(s->fork);
   if (s->lists) cudaFree(s->lists);
+  if (s->res_ctrl) cudaFree(s->res_ctrl);
   if (s->slab2) cudaFree(s->slab2);
   loop_free(s);
   if (s->ctrl) cudaFree(s->ctrl);
@@ -90,13 +94,11 @@ static void phase_free(mpcv_phase_state* s) {
 }
 
 // pipes for a batch of B problems
-static int phase_pipes_for(long B) {
-  int k = MPCV_PIPES_DEFAULT;
-  if (const char* env = getenv("MPCV_PHASE_PIPES")) { const int v = atoi(env); if (v >= 1) k = v; }
-  if (const char* env = getenv("MPCV_PHASE_HOSTLOOP")) if (env[0] == '1') k = 1;   // the host loop synchronises: one pipe
+static int phase_pipes_for(const mpcv_handle* h, long B) {
+  int k = h->knobs.pipes > 0 ? h->knobs.pipes : MPCV_PIPES_DEFAULT;
+  if (h->knobs.hostloop) k = 1;   // the host loop synchronises: one pipe
   if (k > kMaxPipes) k = kMaxPipes;
-  long min_share = MPCV_PIPE_MIN;
-  if (const char* env = getenv("MPCV_PHASE_PIPE_MIN")) { const long v = atol(env); if (v >= 32) min_share = v; }
+  const long min_share = h->knobs.pipe_min > 0 ? h->knobs.pipe_min : MPCV_PIPE_MIN;
   while (k > 1 && B / k < min_share) --k;
   return k;
 }
@@ -195,8 +197,7 @@ static size_t warp_staged_smem(const mpcv_handle* h) {
 }
 // bit 0: ph_slow_kernel, bit 1: ph_tail_kernel
 static int warp_staged_mask(const mpcv_handle* h) {
-  int mask = 3;
-  if (const char* env = getenv("MPCV_WARP_STAGED")) mask = atoi(env) & 3;
+  const int mask = h->knobs.warp_staged >= 0 ? h->knobs.warp_staged : 3;
   return warp_staged_smem(h) <= h->max_smem_optin ? mask : 0;
 }
 static bool warp_staged(const mpcv_handle* h) { return warp_staged_mask(h) != 0; }
@@ -330,28 +331,82 @@ static int phase_host_loop(mpcv_handle* h, cudaStream_t st) {
   return 0;
 }
 
-// the share of the call's I/O that pipe j works on: problems [b0, b0 + nb)
-static SolveIO phase_sub_io(const mpcv_handle* h, const SolveIO& io, long b0) {
-  SolveIO q = io;
-  const long n = h->n_var, np = h->n_p, ng = h->n_g;
-  if (io.x0) q.x0 = io.x0 + b0 * n;
-  if (io.p) q.p = io.p + b0 * np;
-  if (io.x) q.x = io.x + b0 * n;
-  if (io.f) q.f = io.f + b0;
-  if (io.g) q.g = io.g + b0 * ng;
-  if (io.lam_g) q.lam_g = io.lam_g + b0 * ng;
-  if (io.lam_x) q.lam_x = io.lam_x + b0 * n;
-  if (io.status) q.status = io.status + b0;
-  if (io.iters) q.iters = io.iters + b0;
-  if (io.ns) q.ns = io.ns + b0;
-  return q;
+// ---- resident layout: one persistent kernel per solve (mpcv_resident.cuh) -------------------------------------
+struct ResConfig { int slots, stride; size_t smem; unsigned grid; };
+constexpr size_t kResStaticSmem = 1024;
+// slots per CTA the shared memory of an SM allows with kResMinB CTAs resident (0: the workspace does not fit)
+static int res_slots_fit(const mpcv_handle* h, int ctas_per_sm) {
+  const size_t stride_b = (size_t)(h->L.total | 1) * sizeof(double), tab = ph_rows_offset(h->L);
+  size_t budget = h->smem_per_sm / ctas_per_sm;
+  budget = budget > 1024 ? budget - 1024 : 0;                       // the driver reserves 1 KB per CTA
+  if (budget > h->max_smem_optin) budget = h->max_smem_optin;
+  budget = budget > kResStaticSmem ? budget - kResStaticSmem : 0;   // the kernel's static shared memory (slot states)
+  if (budget < tab + stride_b) return 0;
+  const size_t sl = (budget - tab) / stride_b;
+  return (int)(sl > (size_t)kResMaxSlots ? kResMaxSlots : sl);
+}
+static int res_slots_per_sm(const mpcv_handle* h) {
+  const int a = res_slots_fit(h, kResMinB) * kResMinB;
+  return a > 0 ? a : res_slots_fit(h, 1);
+}
+static int res_config(const mpcv_handle* h, long B, ResConfig* c) {
+  int ctas = kResMinB;
+  int S = res_slots_fit(h, ctas);
+  if (S < 1) { ctas = 1; S = res_slots_fit(h, 1); }
+  if (S < 1) return mpcv_set_error(-ENOMEM, "problem workspace exceeds shared memory; use MPCV_LAYOUT_PHASED");
+  long grid = (long)h->sm_count * ctas;
+  if (grid > B) grid = B;
+  // small batches: spread the problems over the CTAs instead of filling the first few
+  const long per = (B + grid - 1) / grid;
+  if (per < S) S = (int)per;
+  c->slots = S;
+  c->stride = h->L.total | 1;
+  c->smem = ph_rows_offset(h->L) + (size_t)S * c->stride * sizeof(double);
+  c->grid = (unsigned)grid;
+  return 0;
+}
+
+template <class Model>
+static int launch_solve_resident(mpcv_handle* h, const SolveIO& io, long B, cudaStream_t st) {
+  if (B <= 0) return 0;
+  if (B > 0x7fffffffL) return mpcv_set_error(-EINVAL, "batch too large");
+  if (!h->phase) h->phase = new mpcv_phase_state();
+  mpcv_phase_state* s = h->phase;
+  if (!s->res_ctrl) CUDA_OK(cudaMalloc(&s->res_ctrl, sizeof(ResCtrl)));
+  if (!s->res_attr_set) {
+    cudaFuncAttributes fa;
+    CUDA_OK(cudaFuncGetAttributes(&fa, res_solve_kernel<Model>));
+    if (fa.sharedSizeBytes > kResStaticSmem) return mpcv_set_error(-EIO, "resident kernel: static shared memory above its budget");
+    CUDA_OK(cudaFuncSetAttribute(res_solve_kernel<Model>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(h->max_smem_optin - kResStaticSmem)));
+    s->res_attr_set = true;
+  }
+  ResConfig c;
+  if (int rc = res_config(h, B, &c)) return rc;
+  if (const mpcv_host_xfer* xf = h->host_xfer)
+    for (const auto& t : xf->in)
+      if (t.host_src) CUDA_OK(cudaMemcpyAsync(t.dev, t.host_src, B * t.row_bytes, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemsetAsync(s->res_ctrl, 0, sizeof(ResCtrl), st));
+  ResArgs a;
+  a.P = h->P; a.L = h->L; a.io = io; a.ctrl = s->res_ctrl; a.count = io.count; a.index = io.index;
+  a.B = B; a.slots = c.slots; a.stride = c.stride;
+  res_solve_kernel<Model><<<c.grid, kResThreads, c.smem, st>>>(a);
+  CUDA_OK(cudaGetLastError());
+  h->launches++;
+  if (const mpcv_host_xfer* xf = h->host_xfer) {
+    for (const auto& t : xf->out)
+      if (t.host_dst) CUDA_OK(cudaMemcpyAsync(t.host_dst, t.dev, B * t.row_bytes, cudaMemcpyDeviceToHost, st));
+    h->host_xfer_done = true;
+  }
+  return 0;
 }
 
 template <class Model>
 static int launch_solve_phased(mpcv_handle* h, const SolveIO& io, long B, cudaStream_t st) {
   if (B <= 0) return 0;
+  if (h->layout == MPCV_LAYOUT_RESIDENT) return launch_solve_resident<Model>(h, io, B, st);
   if (B > 0x7fffffffL) return mpcv_set_error(-EINVAL, "batch too large");
-  const int K = phase_pipes_for(B);
+  const int K = phase_pipes_for(h, B);
   if (int rc = phase_ensure(h, B, K)) return rc;
   mpcv_phase_state* s = h->phase;
   const size_t smem = phase_smem(h);
@@ -366,8 +421,7 @@ static int launch_solve_phased(mpcv_handle* h, const SolveIO& io, long B, cudaSt
         phase_set_smem(ph_der_kernel<Model>, smem))
       return -EIO;
   }
-  const char* env = getenv("MPCV_PHASE_HOSTLOOP");
-  const bool want_graph = !(env && env[0] == '1') && !s->graph_failed;
+  const bool want_graph = !h->knobs.hostloop && !s->graph_failed;
   if (want_graph) {
     for (int j = 0; j < K && !s->graph_failed; ++j) {
       if (s->pipe[j].exec) continue;
@@ -382,7 +436,9 @@ static int launch_solve_phased(mpcv_handle* h, const SolveIO& io, long B, cudaSt
   if (want_graph && !s->graph_failed) {
     // contiguous shares (multiples of 32 problems, so each share starts on a slab block); pipe 0 runs on the
     // caller's stream, the others fork from it and join it again
-    const long share = ((B + K - 1) / K + 31) / 32 * 32;
+    const long share = ph_share_of(B, K);
+    const int tail_cap = h->knobs.tail_cap >= 0 ? h->knobs.tail_cap : kTailBelow;
+    const int tail_shift = h->knobs.tail_shift >= 0 ? h->knobs.tail_shift : MPCV_TAIL_SHIFT;
     if (K > 1) CUDA_OK(cudaEventRecord(s->fork, st));
     for (int j = 0; j < K; ++j) {
       const long b0 = j * share, nb = (b0 + share <= B) ? share : B - b0;
@@ -393,7 +449,7 @@ static int launch_solve_phased(mpcv_handle* h, const SolveIO& io, long B, cudaSt
       if (const mpcv_host_xfer* xf = h->host_xfer)
         for (const auto& t : xf->in)
           if (t.host_src) CUDA_OK(cudaMemcpyAsync(t.dev + b0 * t.row_bytes, t.host_src + b0 * t.row_bytes, nb * t.row_bytes, cudaMemcpyHostToDevice, qs));
-      ph_begin_kernel<<<1, 1, 0, qs>>>(q.ctrl, q.d_io, phase_sub_io(h, io, b0), (int)nb, ph_tail_below((int)nb));
+      ph_begin_kernel<<<1, 1, 0, qs>>>(q.ctrl, q.d_io, io, B, j, K, tail_cap, tail_shift);
       CUDA_OK(cudaGraphLaunch(q.exec, qs));
       if (const mpcv_host_xfer* xf = h->host_xfer)
         for (const auto& t : xf->out)
@@ -414,7 +470,9 @@ static int launch_solve_phased(mpcv_handle* h, const SolveIO& io, long B, cudaSt
   if (const mpcv_host_xfer* xf = h->host_xfer)
     for (const auto& t : xf->in)
       if (t.host_src) CUDA_OK(cudaMemcpyAsync(t.dev, t.host_src, B * t.row_bytes, cudaMemcpyHostToDevice, st));
-  ph_begin_kernel<<<1, 1, 0, st>>>(s->pipe[0].ctrl, s->pipe[0].d_io, io, (int)B, ph_tail_below((int)B));
+  ph_begin_kernel<<<1, 1, 0, st>>>(s->pipe[0].ctrl, s->pipe[0].d_io, io, B, 0, 1,
+                                   h->knobs.tail_cap >= 0 ? h->knobs.tail_cap : kTailBelow,
+                                   h->knobs.tail_shift >= 0 ? h->knobs.tail_shift : MPCV_TAIL_SHIFT);
   h->launches++;
   if (int rc = phase_host_loop<Model>(h, st)) return rc;
   if (const mpcv_host_xfer* xf = h->host_xfer) {
@@ -429,7 +487,8 @@ static int launch_solve_phased(mpcv_handle* h, const SolveIO& io, long B, cudaSt
 template <class Model>
 static int launch_loop_phased(mpcv_handle* h, const LoopIO& io, long B, cudaStream_t st) {
   if (B <= 0) return 0;
-  if (int rc = phase_ensure(h, B, phase_pipes_for(B))) return rc;
+  if (h->layout == MPCV_LAYOUT_RESIDENT) { if (!h->phase) h->phase = new mpcv_phase_state(); }
+  else if (int rc = phase_ensure(h, B, phase_pipes_for(h, B))) return rc;
   mpcv_phase_state* s = h->phase;
   if (B > s->lb_cap) {
     loop_free(s);
@@ -445,6 +504,10 @@ static int launch_loop_phased(mpcv_handle* h, const LoopIO& io, long B, cudaStre
     CUDA_OK(cudaMalloc(&s->lb.steps, B * sizeof(int)));
     CUDA_OK(cudaMalloc(&s->lb.iters_total, B * sizeof(int)));
     CUDA_OK(cudaMalloc(&s->lb.worst, B * sizeof(int)));
+    CUDA_OK(cudaMalloc(&s->lb.xctrl, B * nx * sizeof(double)));
+    CUDA_OK(cudaMalloc(&s->lb.index, B * sizeof(int)));
+    CUDA_OK(cudaMalloc(&s->lb.count, sizeof(int)));
+    CUDA_OK(cudaMalloc(&s->lb.t0, sizeof(long long)));
     s->lb_cap = B;
   }
   const LoopBufs lb = s->lb;
@@ -453,7 +516,9 @@ static int launch_loop_phased(mpcv_handle* h, const LoopIO& io, long B, cudaStre
   h->launches++;
   long long* const lat = h->latency_ns;
   h->latency_ns = nullptr;
-  const SolveIO sio{lb.x0, io.lbx, io.ubx, lb.p, lb.x, lb.f, nullptr, nullptr, nullptr, lb.status, lb.iters, nullptr};
+  SolveIO sio{lb.x0, io.lbx, io.ubx, lb.p, lb.x, lb.f, nullptr, nullptr, nullptr, lb.status, lb.iters, nullptr};
+  sio.index = lb.index;      // every step solves only the scenarios whose loop is still running
+  sio.count = lb.count;
   int rc = 0;
   for (int t = 0; t < io.n_steps && rc == 0; ++t) {
     lp_prepare_kernel<Model><<<grid, 128, 0, st>>>(h->L, io, lb, B, t);
@@ -488,4 +553,5 @@ static int phase_sweeps(mpcv_handle* h, cudaStream_t st, int* sweeps, int* cumul
 #define MPCV_CAT2(a, b) a##b
 #define MPCV_CAT(a, b) MPCV_CAT2(a, b)
 extern const mpcv_phase_vtable MPCV_CAT(mpcv_phase_vtable_, MPCV_INST_MODEL) = {launch_solve_phased<ModelT>, phase_free,
-                                                                                phase_sweeps, launch_loop_phased<ModelT>};
+                                                                                phase_sweeps, launch_loop_phased<ModelT>,
+                                                                                res_slots_per_sm};

@@ -32,11 +32,6 @@ class util:                              # noqa: N801  (MPCTools spells it mpc.u
     c2d = staticmethod(_problems.c2d)
 
 
-# Test hook (tests/ only): a factory (prob, opts) -> object with the NlpSolver call/stats interface, so that the
-# host logic of this module can be exercised against the CPU oracle in a container without a GPU.
-_SOLVER_FACTORY = None
-
-
 class _Par:
     def __init__(self, owner):
         self._o = owner
@@ -76,11 +71,8 @@ class ControlSolver:
     """What `mpc.nmpc(...)` returns in the scripts (the subset of its surface they use)."""
 
     def __init__(self, prob, nx_user, x0, lb, ub, p, uprev, pglob, opts):
-        if _SOLVER_FACTORY is not None:
-            self._solver = _SOLVER_FACTORY(prob, opts)
-        else:
-            from .solver import nlpsol          # raises without a CUDA device: there is no CPU path
-            self._solver = nlpsol("solver", "ipopt", prob, opts or {"ipopt": {"print_level": 0}})
+        from . import solver as _solver          # nlpsol raises without a CUDA device: there is no CPU path
+        self._solver = _solver.nlpsol("solver", "ipopt", prob, opts or {"ipopt": {"print_level": 0}})
         sp = self.spec = self._solver.spec
         self._du = sp.nx != nx_user                    # Du models carry u_prev as an extra state
         self._nxu = nx_user
@@ -122,17 +114,32 @@ class ControlSolver:
                 v = np.asarray(d["u"], dtype=np.float64).reshape(-1)
                 for k in range(sp.N):
                     dst[k * nz + sp.nx:k * nz + sp.nx + sp.nu] = v
-        # move blocking: Du[t] pinned to 0 from the first t on (the scripts' only use of the Du bounds)
-        if "Du" in lb and "Du" in ub:
+        # Du bounds.  The scripts use them two ways: 'free, then pinned to 0' = move blocking
+        # (Inverted_pendulum/...:34-42, Trajectory_tracking_lateral_error.py) and a finite rate box on a model whose
+        # control IS the increment (test2.py:55-59, problems.frenet_bounds).  Anything else would be silently
+        # dropped by a fixed-structure solver, so it is refused.
+        if ("Du" in lb) != ("Du" in ub):
+            raise NotImplementedError("Du bounds must be given in both lb and ub")
+        if "Du" in lb:
+            if sp.nu != 1:
+                raise NotImplementedError("Du bounds are supported for single-input models only (Frenet bicycle: "
+                                          "use problems.frenet_bounds, where the increment is the control)")
             dl = np.asarray(lb["Du"], dtype=np.float64).reshape(-1)
             du = np.asarray(ub["Du"], dtype=np.float64).reshape(-1)
-            if dl.size == sp.N * sp.nu and sp.nu == 1:
-                pinned = (dl == 0) & (du == 0)
-                ntu = int(np.argmax(pinned)) if pinned.any() else 0
-                if pinned.any() and not pinned[ntu:].all():
-                    raise NotImplementedError("Du bounds other than 'free, then pinned to 0' are outside the hot path")
-                if ntu != self.spec.ntu:
-                    raise ValueError("model was built with ntu=%d but the Du bounds pin from t=%d" % (self.spec.ntu, ntu))
+            if dl.size != sp.N * sp.nu or du.size != sp.N * sp.nu:
+                raise ValueError("Du bounds must have Nt*Nu = %d entries" % (sp.N * sp.nu))
+            pinned = (dl == 0) & (du == 0)
+            free = np.isneginf(dl) & np.isposinf(du)
+            if not np.all(pinned | free):
+                raise NotImplementedError("finite Du rate bounds are outside the hot path (only 'free, then pinned "
+                                          "to 0' = move blocking)")
+            ntu = int(np.argmax(pinned)) if pinned.any() else 0
+            if pinned.any() and not pinned[ntu:].all():
+                raise NotImplementedError("Du bounds other than 'free, then pinned to 0' are outside the hot path")
+            if ntu != self.spec.ntu:
+                raise ValueError("model was built with ntu=%d but the Du bounds pin from t=%d" % (self.spec.ntu, ntu))
+        elif self.spec.ntu > 0:
+            raise ValueError("model was built with ntu=%d but no Du bounds pin the later moves" % self.spec.ntu)
         return lo, hi
 
     def _x_aug(self):

@@ -28,6 +28,10 @@ def _ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def _addr(t):
+    return None if t is None else t.data_ptr()
+
+
 class _Handle:
     def __init__(self, spec):
         self.lib = _lib.lib()
@@ -47,7 +51,10 @@ class _Handle:
 
 
 class NlpSolver:
-    """Callable returned by `nlpsol`; mirrors the CasADi `Function` the scripts call."""
+    """Callable returned by `nlpsol`; mirrors the CasADi `Function` the scripts call.
+
+    One call at a time per solver: the workspaces, lists and CUDA graphs belong to the handle, so a call issued
+    on another stream waits on the device for the solver's previous call (see include/mpcv.h)."""
 
     def __init__(self, name, prob, opts=None, device=None):
         if not (isinstance(prob, dict) and "spec" in prob):
@@ -61,6 +68,9 @@ class NlpSolver:
         self.spec = spec
         if not torch.cuda.is_available():
             raise _lib.MpcvError("mpc_verde_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        if spec.ntu > 0 and spec.model not in (5, 6, 7):
+            raise ValueError("ntu > 0 (move blocking) needs a model with u_prev in its state: build it with "
+                             "linear_tracking(..., ntu=K) / R1=..., not the plain linear models")
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         with torch.cuda.device(self.device):
             self._handle = _Handle(spec)
@@ -102,6 +112,10 @@ class NlpSolver:
         return self._phase_counts()[1]
 
     # -- argument normalisation ---------------------------------------------------------------
+    @staticmethod
+    def _is_per_problem(a):
+        return a is not None and not np.isscalar(a) and getattr(a, "ndim", np.ndim(a)) == 2 and np.shape(a)[0] > 1
+
     def _vec(self, a, n, fill, name, device):
         """bounds: scalar-broadcast allowed (e.g. lbg=-inf, single_shooting_v1.py:141)."""
         if a is None:
@@ -158,6 +172,10 @@ class NlpSolver:
         the scripts read only sol['x']); skipping the rest saves their device->host copies."""
         if p is None:
             raise ValueError("p is required")
+        if lam_x0 is not None or lam_g0 is not None:
+            import warnings
+            warnings.warn("lam_x0 / lam_g0 are ignored: like IPOPT without warm_start_init_point the solver starts "
+                          "from z = 1 and least-squares constraint multipliers", stacklevel=2)
         self._check_g_bounds(lbg, ubg)
         n, ng, npar = self.spec.n_var, self.spec.n_g, self.spec.n_p
         on_device = isinstance(p, torch.Tensor) and p.is_cuda
@@ -172,13 +190,32 @@ class NlpSolver:
             if x0t.shape[0] != B:
                 raise ValueError("x0 batch %d != p batch %d" % (x0t.shape[0], B))
         lib, h = self._handle.lib, self._handle.h
+        # one lbx / ubx per problem ([B, n]: a batch of reference calls with different boxes) or one for the batch
+        per_problem = self._is_per_problem(lbx) or self._is_per_problem(ubx)
+        if isinstance(p, torch.Tensor) and p.is_cuda and p.device != self.device:
+            raise ValueError("p lives on %s but the solver was created on %s" % (p.device, self.device))
+        if per_problem and not on_device:
+            pt, on_device = pt.to(self.device), True          # (the host-pointer C entry takes shared bounds only)
+            to_host = True
+        else:
+            to_host = False
         if on_device:
             dev = pt.device
             with torch.cuda.device(dev):
                 pt = pt.contiguous()
                 x0d = None if x0t is None else x0t.to(dev).contiguous()
-                lb = self._vec(lbx, n, -math.inf, "lbx", dev)
-                ub = self._vec(ubx, n, math.inf, "ubx", dev)
+                if per_problem:
+                    def rows(a, fill, name):
+                        if self._is_per_problem(a):
+                            t, _ = self._batched(a, n, name)
+                            if t.shape[0] != B:
+                                raise ValueError("%s batch %d != p batch %d" % (name, t.shape[0], B))
+                            return t.to(dev).contiguous()
+                        return self._vec(a, n, fill, name, dev).reshape(1, n).expand(B, n).contiguous()
+                    lb, ub = rows(lbx, -math.inf, "lbx"), rows(ubx, math.inf, "ubx")
+                else:
+                    lb = self._vec(lbx, n, -math.inf, "lbx", dev)
+                    ub = self._vec(ubx, n, math.inf, "ubx", dev)
                 out = {
                     "x": torch.empty((B, n), dtype=torch.float64, device=dev),
                     "f": torch.empty((B,), dtype=torch.float64, device=dev),
@@ -192,10 +229,14 @@ class NlpSolver:
                 for k in ("g", "lam_g", "lam_x"):
                     if k not in outputs:
                         del out[k]
-                rc = lib.mpcv_solve(h, _ptr(x0d), _ptr(lb), _ptr(ub), _ptr(pt), _ptr(out["x"]), _ptr(out["f"]),
-                                    _ptr(out.get("g")), _ptr(out.get("lam_g")), _ptr(out.get("lam_x")), _ptr(status),
-                                    _ptr(iters), C.c_int64(B), stream)
+                entry = lib.mpcv_solve_bounds if per_problem else lib.mpcv_solve
+                rc = entry(h, _ptr(x0d), _ptr(lb), _ptr(ub), _ptr(pt), _ptr(out["x"]), _ptr(out["f"]),
+                           _ptr(out.get("g")), _ptr(out.get("lam_g")), _ptr(out.get("lam_x")), _ptr(status),
+                           _ptr(iters), C.c_int64(B), stream)
                 _lib.check(rc, "mpcv_solve")
+                if to_host:
+                    out = {k: v.cpu().numpy() for k, v in out.items()}
+                    status, iters = status.cpu().numpy(), iters.cpu().numpy()
         else:
             # host buffers: one C-ABI call does H2D, solve, D2H.  Page-locked inputs (torch pin_memory) are
             # copied straight from the caller's memory; the results then land in page-locked arrays cached
@@ -295,32 +336,52 @@ class NlpSolver:
 
     # -- batched closed loop ---------------------------------------------------------------------------
     def closed_loop(self, x_init, pglob=None, ptraj=None, lbx=None, ubx=None, n_steps=100, warm_mode=WARM_SHIFT,
-                    stop_radius=0.0):
+                    stop_radius=0.0, pglob_traj=None, x0_from_prediction=False, windows=False, horizons=False,
+                    step_times=False):
         """The scripts' MPC loop, batched and on device: solve -> apply u0 -> plant step with the
         same discretisation -> shifted guess (multiple_shooting_casadi.py:224-298,
         single_shooting_v1.py:164-214).  Returns the histories the scripts keep
         (states [B, n_steps+1, nx], applied controls [B, n_steps, nu]) plus per-problem
-        step / iteration counts and the first non-zero solver status."""
+        step / iteration counts and the first non-zero solver status.
+
+        pglob_traj [B, n_steps, npg]: the model of every step (the LTV scripts re-discretise Ac(c[t]) per step,
+        Trjectory_tracking_le_LTV.py:126-143).  x0_from_prediction: the next x0 is the solver's predicted x_1
+        (`solver.fixvar("x",0,solver.var["x",1])`, Trajectory_tracking.py:111-112) while the plant is simulated
+        on.  windows: ptraj is [B, n_steps, N, nps], one horizon window per step (the scripts' par[:, k, t]).
+        horizons / step_times: also return the predicted horizon of every solve (`cat_states`,
+        single_shooting_v1.py:185-188) and the device-timed duration of every MPC step in ms (`times`, :209-212)."""
         s = self.spec
         dev = self.device
         to_np = not (isinstance(x_init, torch.Tensor) and x_init.is_cuda)
         xi, unb = self._batched(x_init, s.nx, "x_init")
         B = xi.shape[0]
+
+        def dev_t(a):
+            t = a if isinstance(a, torch.Tensor) else torch.as_tensor(np.asarray(a, dtype=np.float64))
+            return t.to(dtype=torch.float64)
+
         with torch.cuda.device(dev):
             xi = xi.to(dev).contiguous()
-            pg = None
-            if s.npg > 0:
+            pg = pgt = None
+            if s.npg > 0 and pglob_traj is not None:
+                pgt = dev_t(pglob_traj)
+                if pgt.dim() == 2:
+                    pgt = pgt.unsqueeze(0)
+                if pgt.shape[1] != n_steps or pgt.shape[2] != s.npg:
+                    raise ValueError("pglob_traj must be [B, n_steps, npg] = [*, %d, %d]" % (n_steps, s.npg))
+                pgt = pgt.expand(B, -1, -1).to(dev).contiguous()
+            elif s.npg > 0:
                 pg, _ = self._batched(pglob, s.npg, "pglob")
                 pg = pg.expand(B, s.npg).to(dev).contiguous()
             pt = None
             if s.nps > 0:
-                pt = ptraj if isinstance(ptraj, torch.Tensor) else torch.as_tensor(np.asarray(ptraj, dtype=np.float64))
-                pt = pt.to(dtype=torch.float64)
-                if pt.dim() == 2:
+                pt = dev_t(ptraj)
+                want = (n_steps, s.N, s.nps) if windows else (n_steps + s.N, s.nps)
+                if pt.dim() == len(want):
                     pt = pt.unsqueeze(0)
-                if pt.shape[1] != n_steps + s.N or pt.shape[2] != s.nps:
-                    raise ValueError("ptraj must be [B, n_steps+N, nps] = [*, %d, %d]" % (n_steps + s.N, s.nps))
-                pt = pt.expand(B, -1, -1).to(dev).contiguous()
+                if tuple(pt.shape[1:]) != want:
+                    raise ValueError("ptraj must be [B, %s]" % ", ".join(str(v) for v in want))
+                pt = pt.expand(B, *want).to(dev).contiguous()
             lb = self._vec(lbx, s.n_var, -math.inf, "lbx", dev)
             ub = self._vec(ubx, s.n_var, math.inf, "ubx", dev)
             states = torch.empty((B, n_steps + 1, s.nx), dtype=torch.float64, device=dev)
@@ -328,13 +389,24 @@ class NlpSolver:
             steps = torch.empty((B,), dtype=torch.int32, device=dev)
             iters = torch.empty((B,), dtype=torch.int32, device=dev)
             status = torch.empty((B,), dtype=torch.int32, device=dev)
+            hor = torch.zeros((B, n_steps, s.N + 1, s.nx), dtype=torch.float64, device=dev) if horizons else None
+            tns = torch.zeros((n_steps,), dtype=torch.int64, device=dev) if step_times else None
+            a = _lib.LoopArgs()
+            a.x_init, a.pglob, a.pglob_traj, a.ptraj = xi.data_ptr(), _addr(pg), _addr(pgt), _addr(pt)
+            a.lbx, a.ubx = lb.data_ptr(), ub.data_ptr()
+            a.n_steps, a.warm_mode, a.stop_radius = n_steps, warm_mode, stop_radius
+            a.flags = (1 if x0_from_prediction else 0) | (2 if windows else 0)
+            a.out_states, a.out_controls = states.data_ptr(), controls.data_ptr()
+            a.out_steps, a.out_iters, a.out_status = steps.data_ptr(), iters.data_ptr(), status.data_ptr()
+            a.out_horizons, a.out_step_ns = _addr(hor), _addr(tns)
             stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-            rc = self._handle.lib.mpcv_closed_loop(self._handle.h, _ptr(xi), _ptr(pg), _ptr(pt), _ptr(lb), _ptr(ub),
-                                                   C.c_int32(n_steps), C.c_int32(warm_mode), C.c_double(stop_radius),
-                                                   _ptr(states), _ptr(controls), _ptr(steps), _ptr(iters), _ptr(status),
-                                                   C.c_int64(B), stream)
-            _lib.check(rc, "mpcv_closed_loop")
+            rc = self._handle.lib.mpcv_closed_loop_ex(self._handle.h, C.byref(a), C.c_int64(B), stream)
+            _lib.check(rc, "mpcv_closed_loop_ex")
         out = {"states": states, "controls": controls, "steps": steps, "iters": iters, "status": status}
+        if horizons:
+            out["horizons"] = hor
+        if step_times:
+            out["step_ms"] = tns.to(torch.float64) / 1e6
         if to_np:
             out = {k: v.cpu().numpy() for k, v in out.items()}
         return out

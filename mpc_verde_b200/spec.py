@@ -26,6 +26,7 @@ LAYOUT_AUTO = 0
 LAYOUT_THREAD = 1
 LAYOUT_WARP = 2
 LAYOUT_PHASED = 3
+LAYOUT_RESIDENT = 4
 
 # IPOPT ApplicationReturnStatus names, as CasADi reports them in solver.stats()['return_status']
 STATUS_NAMES = {
@@ -74,6 +75,10 @@ class Spec(C.Structure):
         ("constr_viol_tol", C.c_double),
         ("compl_inf_tol", C.c_double),
         ("extra", C.c_double * 4),
+        ("acceptable_tol", C.c_double),
+        ("acceptable_iter", C.c_int32),
+        ("reserved_", C.c_int32),
+        ("acceptable_obj_change_tol", C.c_double),
     ]
 
     # -- derived sizes -----------------------------------------------------------------
@@ -116,6 +121,14 @@ class Spec(C.Structure):
         return s
 
 
+# options of the scripts' `opts['ipopt']` dicts (Casadi/single_shooting_v1.py:121-129) the solver implements, and
+# the ones that do not change the result (printing)
+IPOPT_OPTIONS = ("tol", "max_iter", "max_soc", "mu_init", "bound_push", "bound_frac", "bound_relax_factor",
+                 "nlp_scaling_max_gradient", "dual_inf_tol", "constr_viol_tol", "compl_inf_tol", "acceptable_tol",
+                 "acceptable_iter", "acceptable_obj_change_tol")
+IPOPT_INERT = ("print_level", "sb", "print_timing_statistics", "max_cpu_time")
+
+
 def ipopt_defaults(s, opts=None):
     """IPOPT 3.12 defaults; `opts` is the {'ipopt': {...}} dict of the scripts
     (Casadi/single_shooting_v1.py:121-129)."""
@@ -130,13 +143,21 @@ def ipopt_defaults(s, opts=None):
     s.dual_inf_tol = 1.0
     s.constr_viol_tol = 1e-4
     s.compl_inf_tol = 1e-4
+    s.acceptable_tol = 1e-6
+    s.acceptable_iter = 15
+    s.acceptable_obj_change_tol = 1e20
     if opts:
         ip = opts.get("ipopt", opts)
         for k in ("tol", "max_iter", "max_soc", "mu_init", "bound_push", "bound_frac",
                   "bound_relax_factor", "nlp_scaling_max_gradient", "dual_inf_tol",
-                  "constr_viol_tol", "compl_inf_tol"):
+                  "constr_viol_tol", "compl_inf_tol", "acceptable_tol", "acceptable_iter",
+                  "acceptable_obj_change_tol"):
             if k in ip:
                 setattr(s, k, ip[k])
+        unknown = set(ip) - set(IPOPT_OPTIONS) - set(IPOPT_INERT) - {"ipopt", "layout", "print_time"}
+        if unknown:
+            import warnings
+            warnings.warn("ipopt options ignored by the GPU solver: %s" % sorted(unknown), stacklevel=3)
     return s
 
 
@@ -187,6 +208,10 @@ def linear_tracking(nx, N, Q, R, T=0.0, R1=None, ntu=0, opts=None):
     """MPCTools linear trackers: Trajectory_tracking_lateral_error.py:17-75 (nx=3),
     Trajectory_tracking_dynamic_model.py:17-141 (nx=4),
     Inverted_pendulum/inverted_pendulum_single_shooting_mpctools.py:10-64 (nx=4, Du cost)."""
+    if R1 is None and ntu > 0:
+        # move blocking needs u_prev in the state (MPCTools: Du[t >= Ntu] = 0): the Du model with a zero rate weight,
+        # e.g. Trajectory_tracking_lateral_error.py:17-18 (Ntu = 3, no Du cost).  The plain models would ignore ntu.
+        R1 = 0.0
     if R1 is None:
         model = {3: MODEL_LINEAR3, 4: MODEL_LINEAR4}[nx]
         R1 = 0.0

@@ -417,6 +417,10 @@ struct IpmOptions {
   double tol, mu_init, bound_push, bound_frac, bound_relax_factor, scal_max_grad;
   double dual_inf_tol, constr_viol_tol, compl_inf_tol;
   int max_iter, max_soc;
+  // acceptable-level termination (IpOptErrorConvCheck::CurrentIsAcceptable)
+  double acceptable_tol = 1e-6, acceptable_obj_change_tol = 1e20, acceptable_dual_inf_tol = 1e10,
+         acceptable_constr_viol_tol = 1e-2, acceptable_compl_inf_tol = 1e-2;
+  int acceptable_iter = 15;
   double kappa_eps = 10.0;        // barrier_tol_factor
   double kappa_mu = 0.2;          // mu_linear_decrease_factor
   double theta_mu = 1.5;          // mu_superlinear_decrease_power
@@ -446,6 +450,9 @@ IpmOptions options_from_spec(const mpcv_spec& s) {
   o.dual_inf_tol = s.dual_inf_tol > 0 ? s.dual_inf_tol : 1.0;
   o.constr_viol_tol = s.constr_viol_tol > 0 ? s.constr_viol_tol : 1e-4;
   o.compl_inf_tol = s.compl_inf_tol > 0 ? s.compl_inf_tol : 1e-4;
+  o.acceptable_tol = s.acceptable_tol > 0 ? s.acceptable_tol : 1e-6;
+  o.acceptable_iter = s.acceptable_iter != 0 ? s.acceptable_iter : 15;
+  o.acceptable_obj_change_tol = s.acceptable_obj_change_tol > 0 ? s.acceptable_obj_change_tol : 1e20;
   return o;
 }
 
@@ -848,6 +855,8 @@ class Ipm {
 
     st = SolveStats();
     st.df = df;
+    int acc_count = 0;
+    double f_last = -1e50;     // IPOPT: last_obj_val_ starts at -1e50
     for (int iter = 0;; ++iter) {
       st.iters = iter;
       // --- convergence test (IpOptErrorConvCheck) ---
@@ -859,6 +868,13 @@ class Ipm {
         double dual_u = e0.dual * sd / df, compl_u = e0.compl_mu * sc / df;
         if (E0 <= opt.tol && dual_u <= opt.dual_inf_tol && e0.prim <= opt.constr_viol_tol &&
             compl_u <= opt.compl_inf_tol) { st.status = MPCV_SOLVE_SUCCEEDED; break; }
+        // acceptable level: acceptable_iter consecutive iterates within the acceptable tolerances
+        const bool acc = opt.acceptable_iter > 0 && E0 <= opt.acceptable_tol && dual_u <= opt.acceptable_dual_inf_tol &&
+                         e0.prim <= opt.acceptable_constr_viol_tol && compl_u <= opt.acceptable_compl_inf_tol &&
+                         std::fabs(f_curr - f_last) / std::max(1.0, std::fabs(f_curr)) <= opt.acceptable_obj_change_tol;
+        f_last = f_curr;
+        if (acc) { if (++acc_count >= opt.acceptable_iter) { st.status = MPCV_SOLVED_TO_ACCEPTABLE_LEVEL; break; } }
+        else acc_count = 0;
       }
       if (iter >= opt.max_iter) { st.status = MPCV_MAXIMUM_ITERATIONS_EXCEEDED; break; }
       if (!std::isfinite(E0)) { st.status = MPCV_INVALID_NUMBER_DETECTED; break; }

@@ -6,6 +6,7 @@ import numpy as np
 
 from mpc_verde_b200 import problems
 from mpc_verde_b200 import spec as S
+from tests import reference_loops
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -54,7 +55,7 @@ def lateral_error_closed_loop(solve_fn, ltv, nsim=None):
     Nsim = a.size if nsim is None else nsim
     sp = S.linear_tracking(3, Nt, Q=(10.0, 1.0, 0.0), R=0.01, T=Delta, R1=0.0, ntu=1)
     lbx, ubx = problems.control_box(sp, -0.3491, 0.3491)
-    par = problems.lateral_error_par(a, b, Nt, Delta)
+    par = reference_loops.lateral_error_par(a, b, Nt, Delta)
     x = np.zeros((Nsim + 1, 3))
     u = np.zeros(Nsim)
     for t in range(Nsim):

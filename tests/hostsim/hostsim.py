@@ -10,14 +10,16 @@ _CSRC = os.path.join(_HERE, "..", "..", "mpc_verde_b200", "csrc")
 _LIB = None
 
 
-def build():
-    so = os.path.join(_HERE, "libhostsim.so")
+def build(lanes=False):
+    """lanes=True: the lane-parallel Riccati factorisation (riccati_factor_lanes) replayed with one lane."""
+    so = os.path.join(_HERE, "libhostsim_lanes.so" if lanes else "libhostsim.so")
     deps = [os.path.join(_HERE, "hostsim.cpp")] + [
         os.path.join(_CSRC, f) for f in ("mpcv_models.cuh", "mpcv_ipm.cuh", "mpcv_driver.cuh", "mpcv_phase.cuh",
                                          "mpcv_params.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas",
-                               "-ffp-contract=off", "-x", "c++", os.path.join(_HERE, "hostsim.cpp"), "-o", so])
+                               "-ffp-contract=off"] + (["-DMPCV_HOST_LANE_RICCATI"] if lanes else []) +
+                              ["-x", "c++", os.path.join(_HERE, "hostsim.cpp"), "-o", so])
     return so
 
 

@@ -1,10 +1,11 @@
 """The MPCTools-shaped front end (mpc_verde_b200/mpctools.py) driven the way the reference scripts drive
-MPCTools.  Host logic on the CPU (the oracle stands in for the GPU solver through the module's test hook);
+MPCTools.  Host logic on the CPU (the oracle stands in for the GPU solver: the tests patch solver.nlpsol);
 the same loops on the GPU in test_gpu_parity-style tests below (marked gpu)."""
 import numpy as np
 import pytest
 
 from mpc_verde_b200 import mpctools as mpc
+from mpc_verde_b200 import solver as solver_mod
 from mpc_verde_b200 import problems
 from oracle import mpc_oracle as O
 from tests import common
@@ -13,7 +14,7 @@ from tests import common
 class _OracleSolver:
     """NlpSolver interface over the CPU oracle — test infrastructure only."""
 
-    def __init__(self, prob, opts):
+    def __init__(self, name, plugin, prob, opts=None, device=None):       # the signature of solver.nlpsol
         self.spec = prob["spec"].copy()
 
     def __call__(self, x0, lbx, ubx, p, outputs=("x", "f")):
@@ -56,7 +57,7 @@ def pendulum_script(nsim, batch=None):
 
 
 def test_pendulum_script_through_the_front_end_cpu(monkeypatch):
-    monkeypatch.setattr(mpc, "_SOLVER_FACTORY", _OracleSolver)
+    monkeypatch.setattr(solver_mod, "nlpsol", _OracleSolver)
     g = common.golden("pendulum_invertpend.csv")
     xcl, ucl = pendulum_script(40)
     assert abs(ucl[0, 0] - (-60.84425718936204)) <= 1e-5
@@ -68,7 +69,7 @@ def test_pendulum_script_through_the_front_end_cpu(monkeypatch):
 
 def test_controlsolver_surface_cpu(monkeypatch):
     """par / solve / stats / saveguess / fixvar(x1) / var — the loop of Trajectory Tracking/Trajectory_tracking.py:101-118."""
-    monkeypatch.setattr(mpc, "_SOLVER_FACTORY", _OracleSolver)
+    monkeypatch.setattr(solver_mod, "nlpsol", _OracleSolver)
     Nt = 10
     model = problems.unicycle_tracking(N=Nt, T=0.2, M=1)
     lb = {"u": np.array([-1, -np.pi / 4]), "x": np.array([-20, -2, -np.inf])}

