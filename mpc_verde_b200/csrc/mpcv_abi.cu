@@ -157,10 +157,13 @@ mpcv_handle* mpcv_create(const mpcv_spec* s) {
   h->max_smem_optin = prop.sharedMemPerBlockOptin;
   h->smem_per_sm = prop.sharedMemPerMultiprocessor;
   h->layout = s->layout;
-  // AUTO: the slab pipeline for multiple shooting, one thread per problem for single shooting.  The CTA-resident
-  // layout is opt-in: it cuts the DRAM traffic of a solve 480x but is latency-bound (profiles/r2b_*).
+  // AUTO: one thread per problem for single shooting; multiple shooting: the CTA-resident kernel for batches below
+  // the crossover (it is latency-bound: 26 problems per SM), the slab pipeline above it (profiles/r2b_*).
   const int res_slots = mpcv_phase_vtable_of(s->model)->res_slots_per_sm(h);
-  if (h->layout == MPCV_LAYOUT_AUTO) h->layout = h->single ? MPCV_LAYOUT_THREAD : MPCV_LAYOUT_PHASED;
+  if (h->layout == MPCV_LAYOUT_AUTO) {
+    h->layout = h->single ? MPCV_LAYOUT_THREAD : MPCV_LAYOUT_PHASED;
+    h->layout_auto = !h->single;       // per call: the resident kernel below the crossover batch, the pipeline above
+  }
   if (h->layout == MPCV_LAYOUT_RESIDENT && res_slots < 1) h->layout = MPCV_LAYOUT_PHASED;
   if (h->single) h->layout = MPCV_LAYOUT_THREAD;
   if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess ||

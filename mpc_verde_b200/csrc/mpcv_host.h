@@ -32,8 +32,8 @@ struct mpcv_host_xfer {
 // tuning overrides from the environment (they exist for the A/B measurements quoted in DESIGN.md and for the tests);
 // read ONCE, when a handle is created, never on the launch path.  -1 = the compiled-in default.
 struct mpcv_knobs {
-  int tail_cap = -1, tail_shift = -1, pipes = -1, warp_staged = -1;
-  long pipe_min = -1;
+  int tail_cap = -1, tail_shift = -1, pipes = -1, warp_staged = -1, res_tail = -1;
+  long pipe_min = -1, resident_below = -1;
   bool hostloop = false;
 };
 inline mpcv_knobs mpcv_knobs_from_env() {
@@ -44,6 +44,8 @@ inline mpcv_knobs mpcv_knobs_from_env() {
   if (const char* env = getenv("MPCV_PHASE_PIPE_MIN")) { const long v = atol(env); if (v >= 32) k.pipe_min = v; }
   if (const char* env = getenv("MPCV_PHASE_HOSTLOOP")) k.hostloop = env[0] == '1';
   if (const char* env = getenv("MPCV_WARP_STAGED")) k.warp_staged = atoi(env) & 3;
+  if (const char* env = getenv("MPCV_RES_TAIL")) k.res_tail = atoi(env);                 // 0: ph_tail_kernel
+  if (const char* env = getenv("MPCV_RESIDENT_BELOW")) k.resident_below = atol(env);     // AUTO: resident below this batch
   return k;
 }
 
@@ -53,7 +55,8 @@ struct mpcv_handle {
   mpcv::Layout L;
   int nx, nu, n_var, n_g, n_p, npg, nps;
   bool single;
-  int layout;            // resolved MPCV_LAYOUT_*
+  int layout;            // resolved MPCV_LAYOUT_* (AUTO for multiple shooting: PHASED here, decided per call by batch size)
+  bool layout_auto = false;
   int device;
   int sm_count;
   size_t max_smem_optin;

@@ -803,8 +803,9 @@ static __global__ void ph_flip_kernel(PhaseCtrl* ctrl, cudaGraphConditionalHandl
 // scenarios, a device counter.
 __host__ __device__ inline long ph_share_of(long cnt, int K) { return ((cnt + K - 1) / K + 31) / 32 * 32; }
 static __global__ void ph_begin_kernel(PhaseCtrl* ctrl, SolveIO* dst, const SolveIO io, long B_host, int j, int K,
-                                       int tail_cap, int tail_shift) {
+                                       int tail_cap, int tail_shift, int* res_queue_head) {
   *dst = io;
+  if (res_queue_head) *res_queue_head = 0;     // queue of the resident tail kernel (mpcv_resident.cuh)
   const long cnt = io.count ? (long)*io.count : B_host;
   const long share = ph_share_of(cnt, K), e0 = (long)j * share;
   long nb = cnt - e0;

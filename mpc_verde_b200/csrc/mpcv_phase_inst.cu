@@ -223,6 +223,117 @@ static int phase_set_smem(K kern, size_t smem) {
   return 0;
 }
 
+// hand-off threshold of the sweeps: min(B >> shift, cap) active problems.  The resident tail turns a problem over
+// faster than a sweep does once the active set is small, so the hand-off comes earlier with it.
+#ifndef MPCV_RES_TAIL_SHIFT
+#define MPCV_RES_TAIL_SHIFT 2
+#endif
+#ifndef MPCV_RES_TAIL_BELOW
+#define MPCV_RES_TAIL_BELOW 8192
+#endif
+static bool res_tail_usable(const mpcv_handle* h);
+static int res_slots_per_sm(const mpcv_handle* h);
+static int phase_tail_cap(const mpcv_handle* h) {
+  return h->knobs.tail_cap >= 0 ? h->knobs.tail_cap : (res_tail_usable(h) ? MPCV_RES_TAIL_BELOW : kTailBelow);
+}
+static int phase_tail_shift(const mpcv_handle* h) {
+  return h->knobs.tail_shift >= 0 ? h->knobs.tail_shift : (res_tail_usable(h) ? MPCV_RES_TAIL_SHIFT : MPCV_TAIL_SHIFT);
+}
+
+// ---- resident layout: one persistent kernel per solve (mpcv_resident.cuh) -------------------------------------
+struct ResConfig { int slots, stride; size_t smem; unsigned grid; };
+constexpr size_t kResStaticSmem = 1024;
+// slots per CTA the shared memory of an SM allows with kResMinB CTAs resident (0: the workspace does not fit)
+static int res_slots_fit(const mpcv_handle* h, int ctas_per_sm) {
+  const size_t stride_b = (size_t)(h->L.total | 1) * sizeof(double), tab = ph_rows_offset(h->L);
+  size_t budget = h->smem_per_sm / ctas_per_sm;
+  budget = budget > 1024 ? budget - 1024 : 0;                       // the driver reserves 1 KB per CTA
+  if (budget > h->max_smem_optin) budget = h->max_smem_optin;
+  budget = budget > kResStaticSmem ? budget - kResStaticSmem : 0;   // the kernel's static shared memory (slot states)
+  if (budget < tab + stride_b) return 0;
+  const size_t sl = (budget - tab) / stride_b;
+  return (int)(sl > (size_t)kResMaxSlots ? kResMaxSlots : sl);
+}
+static int res_slots_per_sm(const mpcv_handle* h) {
+  const int a = res_slots_fit(h, kResMinB) * kResMinB;
+  return a > 0 ? a : res_slots_fit(h, 1);
+}
+static int res_config(const mpcv_handle* h, long B, ResConfig* c) {
+  int ctas = kResMinB;
+  int S = res_slots_fit(h, ctas);
+  if (S < 1) { ctas = 1; S = res_slots_fit(h, 1); }
+  if (S < 1) return mpcv_set_error(-ENOMEM, "problem workspace exceeds shared memory; use MPCV_LAYOUT_PHASED");
+  long grid = (long)h->sm_count * ctas;
+  if (grid > B) grid = B;
+  // small batches: spread the problems over the CTAs instead of filling the first few
+  const long per = (B + grid - 1) / grid;
+  if (per < S) S = (int)per;
+  c->slots = S;
+  c->stride = h->L.total | 1;
+  c->smem = ph_rows_offset(h->L) + (size_t)S * c->stride * sizeof(double);
+  c->grid = (unsigned)grid;
+  return 0;
+}
+
+// queue heads (one per pipe for the resident tail + one for the stand-alone resident solve) and the kernels' opt-in
+// to large dynamic shared memory
+template <class Model>
+static int res_prepare(mpcv_handle* h) {
+  if (!h->phase) h->phase = new mpcv_phase_state();
+  mpcv_phase_state* s = h->phase;
+  if (!s->res_ctrl) {
+    CUDA_OK(cudaMalloc(&s->res_ctrl, (kMaxPipes + 1) * sizeof(ResCtrl)));
+    CUDA_OK(cudaMemset(s->res_ctrl, 0, (kMaxPipes + 1) * sizeof(ResCtrl)));
+    CUDA_OK(cudaStreamSynchronize(0));
+  }
+  if (!s->res_attr_set) {
+    cudaFuncAttributes fa;
+    CUDA_OK(cudaFuncGetAttributes(&fa, res_solve_kernel<Model, false>));
+    if (fa.sharedSizeBytes > kResStaticSmem) return mpcv_set_error(-EIO, "resident kernel: static shared memory above its budget");
+    CUDA_OK(cudaFuncSetAttribute(res_solve_kernel<Model, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(h->max_smem_optin - kResStaticSmem)));
+    CUDA_OK(cudaFuncSetAttribute(res_solve_kernel<Model, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(h->max_smem_optin - kResStaticSmem)));
+    s->res_attr_set = true;
+  }
+  return 0;
+}
+
+// the stragglers of the sweeps finish in the resident kernel when an SM holds enough problems (else ph_tail_kernel)
+constexpr int kResidentMinSlots = 8;
+static bool res_tail_usable(const mpcv_handle* h) {
+  if (h->knobs.res_tail == 0) return false;
+  return res_slots_per_sm(h) >= kResidentMinSlots;
+}
+// layout of this call: AUTO = the resident kernel for batches below the crossover with the slab pipeline
+// (measured on C2: 3.6 vs 7.2 ms at B = 4,096; 31 vs 16.5 ms at B = 65,536), the pipeline above it
+#ifndef MPCV_RESIDENT_BELOW
+#define MPCV_RESIDENT_BELOW 16384
+#endif
+static int effective_layout(const mpcv_handle* h, long B) {
+  if (!h->layout_auto) return h->layout;
+  const long below = h->knobs.resident_below >= 0 ? h->knobs.resident_below : MPCV_RESIDENT_BELOW;
+  return (B < below && res_slots_per_sm(h) >= kResidentMinSlots) ? MPCV_LAYOUT_RESIDENT : MPCV_LAYOUT_PHASED;
+}
+
+template <class Model>
+static ResArgs res_tail_args(const mpcv_handle* h, int j, const ResConfig& c) {
+  const mpcv_phase_state* s = h->phase;
+  const PhasePipe& q = s->pipe[j];
+  ResArgs a = {};
+  a.P = h->P; a.L = h->L; a.ctrl = s->res_ctrl + j; a.count = nullptr; a.index = nullptr; a.B = 0;
+  a.slots = c.slots; a.stride = c.stride;
+  a.pctrl = q.ctrl; a.io_dev = q.d_io; a.slab[0] = q.slab[0]; a.slab[1] = q.slab[1]; a.act[0] = q.act[0]; a.act[1] = q.act[1];
+  return a;
+}
+// the resident tail of pipe j of K: its share of the CTAs the GPU holds, full slots
+static int res_tail_config(const mpcv_handle* h, int K, ResConfig* c) {
+  if (int rc = res_config(h, (long)h->sm_count * kResMinB * kResMaxSlots, c)) return rc;
+  long grid = (long)h->sm_count * kResMinB / K;
+  c->grid = (unsigned)(grid < 1 ? 1 : grid);
+  return 0;
+}
+
 // ---- graph construction: init chain, then a WHILE node whose body is one iteration sweep ----------
 static int add_kernel(cudaGraph_t g, cudaGraphNode_t* node, cudaGraphNode_t* dep, void* func, unsigned grid,
                       unsigned block, size_t smem, void** args) {
@@ -280,9 +391,18 @@ static int phase_build_graph(mpcv_handle* h, int j) {
   if (int rc = add_kernel(body, &b_slow, &b_accept, (void*)ph_slow_kernel<Model>, gr.warp, kWarpPhaseThreads, warp_smem(h), a_slow)) return rc;
   if (int rc = add_kernel(body, &b_der, &b_slow, (void*)ph_der_kernel<Model>, gr.stage, kPhaseThreads, smem, a_init)) return rc;
   if (int rc = add_kernel(body, &b_flip, &b_der, (void*)ph_flip_kernel, 1, 1, 0, a_flip)) return rc;
-  // the stragglers finish in one persistent kernel after the loop
+  // the stragglers finish in one persistent kernel after the loop: the CTA-resident kernel (their workspaces staged
+  // into shared memory, continuous refill from the active list) when an SM holds enough problems, else one warp each
   cudaGraphNode_t n_tail;
-  if (int rc = add_kernel(g, &n_tail, &n_while, (void*)ph_tail_kernel<Model>, gr.warp, kWarpPhaseThreads, warp_smem(h), a_tail)) return rc;
+  if (res_tail_usable(h)) {
+    ResConfig rc_;
+    if (int rc = res_tail_config(h, h->phase->npipes, &rc_)) return rc;
+    ResArgs ra = res_tail_args<Model>(h, j, rc_);
+    void* a_res[] = {&ra};
+    if (int rc = add_kernel(g, &n_tail, &n_while, (void*)res_solve_kernel<Model, true>, rc_.grid, kResThreads, rc_.smem, a_res)) return rc;
+  } else {
+    if (int rc = add_kernel(g, &n_tail, &n_while, (void*)ph_tail_kernel<Model>, gr.warp, kWarpPhaseThreads, warp_smem(h), a_tail)) return rc;
+  }
   cudaGraphExec_t exec = nullptr;
   CUDA_OK(cudaGraphInstantiate(&exec, g, 0));
   s->graph = g;
@@ -325,44 +445,15 @@ static int phase_host_loop(mpcv_handle* h, cudaStream_t st) {
     CUDA_OK(cudaStreamSynchronize(st));
     if (s->h_ctrl->n_act[s->h_ctrl->sweep & 1] <= s->h_ctrl->tail_below) break;
   }
-  ph_tail_kernel<Model><<<gr.warp, kWarpPhaseThreads, warp_smem(h), st>>>(a, (warp_staged_mask(h) >> 1) & 1);
+  if (res_tail_usable(h)) {
+    ResConfig rc_;
+    if (int rc = res_tail_config(h, 1, &rc_)) return rc;
+    res_solve_kernel<Model, true><<<rc_.grid, kResThreads, rc_.smem, st>>>(res_tail_args<Model>(h, 0, rc_));
+  } else {
+    ph_tail_kernel<Model><<<gr.warp, kWarpPhaseThreads, warp_smem(h), st>>>(a, (warp_staged_mask(h) >> 1) & 1);
+  }
   h->launches++;
   CUDA_OK(cudaGetLastError());
-  return 0;
-}
-
-// ---- resident layout: one persistent kernel per solve (mpcv_resident.cuh) -------------------------------------
-struct ResConfig { int slots, stride; size_t smem; unsigned grid; };
-constexpr size_t kResStaticSmem = 1024;
-// slots per CTA the shared memory of an SM allows with kResMinB CTAs resident (0: the workspace does not fit)
-static int res_slots_fit(const mpcv_handle* h, int ctas_per_sm) {
-  const size_t stride_b = (size_t)(h->L.total | 1) * sizeof(double), tab = ph_rows_offset(h->L);
-  size_t budget = h->smem_per_sm / ctas_per_sm;
-  budget = budget > 1024 ? budget - 1024 : 0;                       // the driver reserves 1 KB per CTA
-  if (budget > h->max_smem_optin) budget = h->max_smem_optin;
-  budget = budget > kResStaticSmem ? budget - kResStaticSmem : 0;   // the kernel's static shared memory (slot states)
-  if (budget < tab + stride_b) return 0;
-  const size_t sl = (budget - tab) / stride_b;
-  return (int)(sl > (size_t)kResMaxSlots ? kResMaxSlots : sl);
-}
-static int res_slots_per_sm(const mpcv_handle* h) {
-  const int a = res_slots_fit(h, kResMinB) * kResMinB;
-  return a > 0 ? a : res_slots_fit(h, 1);
-}
-static int res_config(const mpcv_handle* h, long B, ResConfig* c) {
-  int ctas = kResMinB;
-  int S = res_slots_fit(h, ctas);
-  if (S < 1) { ctas = 1; S = res_slots_fit(h, 1); }
-  if (S < 1) return mpcv_set_error(-ENOMEM, "problem workspace exceeds shared memory; use MPCV_LAYOUT_PHASED");
-  long grid = (long)h->sm_count * ctas;
-  if (grid > B) grid = B;
-  // small batches: spread the problems over the CTAs instead of filling the first few
-  const long per = (B + grid - 1) / grid;
-  if (per < S) S = (int)per;
-  c->slots = S;
-  c->stride = h->L.total | 1;
-  c->smem = ph_rows_offset(h->L) + (size_t)S * c->stride * sizeof(double);
-  c->grid = (unsigned)grid;
   return 0;
 }
 
@@ -372,25 +463,17 @@ static int launch_solve_resident(mpcv_handle* h, const SolveIO& io, long B, cuda
   if (B > 0x7fffffffL) return mpcv_set_error(-EINVAL, "batch too large");
   if (!h->phase) h->phase = new mpcv_phase_state();
   mpcv_phase_state* s = h->phase;
-  if (!s->res_ctrl) CUDA_OK(cudaMalloc(&s->res_ctrl, sizeof(ResCtrl)));
-  if (!s->res_attr_set) {
-    cudaFuncAttributes fa;
-    CUDA_OK(cudaFuncGetAttributes(&fa, res_solve_kernel<Model>));
-    if (fa.sharedSizeBytes > kResStaticSmem) return mpcv_set_error(-EIO, "resident kernel: static shared memory above its budget");
-    CUDA_OK(cudaFuncSetAttribute(res_solve_kernel<Model>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(h->max_smem_optin - kResStaticSmem)));
-    s->res_attr_set = true;
-  }
+  if (int rc = res_prepare<Model>(h)) return rc;
   ResConfig c;
   if (int rc = res_config(h, B, &c)) return rc;
   if (const mpcv_host_xfer* xf = h->host_xfer)
     for (const auto& t : xf->in)
       if (t.host_src) CUDA_OK(cudaMemcpyAsync(t.dev, t.host_src, B * t.row_bytes, cudaMemcpyHostToDevice, st));
-  CUDA_OK(cudaMemsetAsync(s->res_ctrl, 0, sizeof(ResCtrl), st));
-  ResArgs a;
-  a.P = h->P; a.L = h->L; a.io = io; a.ctrl = s->res_ctrl; a.count = io.count; a.index = io.index;
+  CUDA_OK(cudaMemsetAsync(s->res_ctrl + kMaxPipes, 0, sizeof(ResCtrl), st));
+  ResArgs a = {};
+  a.P = h->P; a.L = h->L; a.io = io; a.ctrl = s->res_ctrl + kMaxPipes; a.count = io.count; a.index = io.index;
   a.B = B; a.slots = c.slots; a.stride = c.stride;
-  res_solve_kernel<Model><<<c.grid, kResThreads, c.smem, st>>>(a);
+  res_solve_kernel<Model, false><<<c.grid, kResThreads, c.smem, st>>>(a);
   CUDA_OK(cudaGetLastError());
   h->launches++;
   if (const mpcv_host_xfer* xf = h->host_xfer) {
@@ -404,13 +487,14 @@ static int launch_solve_resident(mpcv_handle* h, const SolveIO& io, long B, cuda
 template <class Model>
 static int launch_solve_phased(mpcv_handle* h, const SolveIO& io, long B, cudaStream_t st) {
   if (B <= 0) return 0;
-  if (h->layout == MPCV_LAYOUT_RESIDENT) return launch_solve_resident<Model>(h, io, B, st);
+  if (effective_layout(h, B) == MPCV_LAYOUT_RESIDENT) return launch_solve_resident<Model>(h, io, B, st);
   if (B > 0x7fffffffL) return mpcv_set_error(-EINVAL, "batch too large");
   const int K = phase_pipes_for(h, B);
   if (int rc = phase_ensure(h, B, K)) return rc;
   mpcv_phase_state* s = h->phase;
   const size_t smem = phase_smem(h);
   if (smem > h->max_smem_optin) return mpcv_set_error(-ENOMEM, "bounds table exceeds shared memory; use MPCV_LAYOUT_WARP");
+  if (res_tail_usable(h)) { if (int rc = res_prepare<Model>(h)) return rc; }
   if (!s->pipe[0].exec && !s->graph_failed) {
     if (phase_set_smem(ph_init_kernel<Model>, smem) || phase_set_smem(ph_der0_kernel<Model>, smem) ||
         phase_set_smem(ph_init2_kernel<Model>, smem) || phase_set_smem(ph_pre_kernel<Model>, smem) ||
@@ -437,8 +521,7 @@ static int launch_solve_phased(mpcv_handle* h, const SolveIO& io, long B, cudaSt
     // contiguous shares (multiples of 32 problems, so each share starts on a slab block); pipe 0 runs on the
     // caller's stream, the others fork from it and join it again
     const long share = ph_share_of(B, K);
-    const int tail_cap = h->knobs.tail_cap >= 0 ? h->knobs.tail_cap : kTailBelow;
-    const int tail_shift = h->knobs.tail_shift >= 0 ? h->knobs.tail_shift : MPCV_TAIL_SHIFT;
+    const int tail_cap = phase_tail_cap(h), tail_shift = phase_tail_shift(h);
     if (K > 1) CUDA_OK(cudaEventRecord(s->fork, st));
     for (int j = 0; j < K; ++j) {
       const long b0 = j * share, nb = (b0 + share <= B) ? share : B - b0;
@@ -449,7 +532,7 @@ static int launch_solve_phased(mpcv_handle* h, const SolveIO& io, long B, cudaSt
       if (const mpcv_host_xfer* xf = h->host_xfer)
         for (const auto& t : xf->in)
           if (t.host_src) CUDA_OK(cudaMemcpyAsync(t.dev + b0 * t.row_bytes, t.host_src + b0 * t.row_bytes, nb * t.row_bytes, cudaMemcpyHostToDevice, qs));
-      ph_begin_kernel<<<1, 1, 0, qs>>>(q.ctrl, q.d_io, io, B, j, K, tail_cap, tail_shift);
+      ph_begin_kernel<<<1, 1, 0, qs>>>(q.ctrl, q.d_io, io, B, j, K, tail_cap, tail_shift, s->res_ctrl ? &s->res_ctrl[j].next : nullptr);
       CUDA_OK(cudaGraphLaunch(q.exec, qs));
       if (const mpcv_host_xfer* xf = h->host_xfer)
         for (const auto& t : xf->out)
@@ -470,9 +553,8 @@ static int launch_solve_phased(mpcv_handle* h, const SolveIO& io, long B, cudaSt
   if (const mpcv_host_xfer* xf = h->host_xfer)
     for (const auto& t : xf->in)
       if (t.host_src) CUDA_OK(cudaMemcpyAsync(t.dev, t.host_src, B * t.row_bytes, cudaMemcpyHostToDevice, st));
-  ph_begin_kernel<<<1, 1, 0, st>>>(s->pipe[0].ctrl, s->pipe[0].d_io, io, B, 0, 1,
-                                   h->knobs.tail_cap >= 0 ? h->knobs.tail_cap : kTailBelow,
-                                   h->knobs.tail_shift >= 0 ? h->knobs.tail_shift : MPCV_TAIL_SHIFT);
+  ph_begin_kernel<<<1, 1, 0, st>>>(s->pipe[0].ctrl, s->pipe[0].d_io, io, B, 0, 1, phase_tail_cap(h), phase_tail_shift(h),
+                                   s->res_ctrl ? &s->res_ctrl[0].next : nullptr);
   h->launches++;
   if (int rc = phase_host_loop<Model>(h, st)) return rc;
   if (const mpcv_host_xfer* xf = h->host_xfer) {
@@ -487,7 +569,7 @@ static int launch_solve_phased(mpcv_handle* h, const SolveIO& io, long B, cudaSt
 template <class Model>
 static int launch_loop_phased(mpcv_handle* h, const LoopIO& io, long B, cudaStream_t st) {
   if (B <= 0) return 0;
-  if (h->layout == MPCV_LAYOUT_RESIDENT) { if (!h->phase) h->phase = new mpcv_phase_state(); }
+  if (effective_layout(h, B) == MPCV_LAYOUT_RESIDENT) { if (!h->phase) h->phase = new mpcv_phase_state(); }
   else if (int rc = phase_ensure(h, B, phase_pipes_for(h, B))) return rc;
   mpcv_phase_state* s = h->phase;
   if (B > s->lb_cap) {

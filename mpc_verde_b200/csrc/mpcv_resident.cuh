@@ -61,6 +61,12 @@ struct ResArgs {
   long B;
   int slots;          // problems resident per CTA
   int stride;         // doubles per slot row
+  // TAIL mode (the stragglers of the phase pipeline): the queue is the pipe's active list, a refill stages the
+  // problem's workspace in from the slab with its solve state, the I/O pointers are the pipe's device copy
+  const PhaseCtrl* pctrl;
+  const SolveIO* io_dev;
+  double* slab[2];
+  const int* act[2];
 };
 
 enum { RS_EMPTY = 0, RS_NEW = 1, RS_RUN = 2, RS_DONE = 3 };
@@ -143,7 +149,7 @@ __device__ __noinline__ void res_slow_path(const Params& P, const Layout& L, dou
   __syncwarp();
 }
 
-template <class Model>
+template <class Model, bool TAIL>
 __global__ void __launch_bounds__(kResThreads, kResMinB) res_solve_kernel(const __grid_constant__ ResArgs a) {
   using R = Resident<Model>;
   using WS = WsShared;
@@ -152,15 +158,23 @@ __global__ void __launch_bounds__(kResThreads, kResMinB) res_solve_kernel(const 
   __shared__ int n_slow, slow_next;
   const Layout& L = a.L;
   const Params& P = a.P;
-  const SolveIO& io = a.io;
-  const int S = a.slots, tid = threadIdx.x, lane = tid & 31;
+  const SolveIO io = TAIL ? *a.io_dev : a.io;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // TAIL: the stragglers the sweeps left in the pipe's active list, their workspaces in the current slab
+  const int tin = TAIL ? (a.pctrl->sweep & 1) : 0;
+  const long B = TAIL ? (long)a.pctrl->n_act[tin] : (a.count ? (long)*a.count : a.B);
+  if (TAIL && (long)blockIdx.x >= B) return;
+  const double* const tslab = TAIL ? a.slab[a.pctrl->cur] : nullptr;
+  const int* const tlist = TAIL ? a.act[tin] : nullptr;
+  // few problems: spread them over the CTAs instead of filling the first ones
+  int S = a.slots;
+  if (TAIL) { const long per = (B + gridDim.x - 1) / gridDim.x; if (per < S) S = (int)(per < 1 ? 1 : per); }
   const BndEntry* tab = ph_bounds_table<Model>(P, L, io);
   double* const rows = reinterpret_cast<double*>(ph_smem + ph_rows_offset(L));
   auto row = [&](int s) { return WS{rows + (long)s * a.stride}; };
   for (int s = tid; s < kResMaxSlots; s += blockDim.x) { sstate[s] = s < S ? RS_EMPTY : RS_DONE; sslow[s] = 0; }
   if (tid == 0) { n_slow = 0; slow_next = 0; }
   __syncthreads();
-  const long B = a.count ? (long)*a.count : a.B;
   constexpr int GL = kResGL, RL = kResRL;
   const int ggrp = tid / GL, ngg = kResThreads / GL;
   const int rgrp = tid / RL, nrg = kResThreads / RL;
@@ -185,10 +199,23 @@ __global__ void __launch_bounds__(kResThreads, kResMinB) res_solve_kernel(const 
           if (gg.lane == 0) e = atomicAdd(&a.ctrl->next, 1);
           e = gg.bcast(e);
           if (e < B) {
-            const long b = a.index ? (long)a.index[e] : (long)e;
             gg.sync();
-            R::load_body(P, L, ws, io, b, tab, gg, io.ns ? ph_globaltimer() : 0);
-            state = RS_NEW;
+            if (TAIL) {
+              // the problem comes with its iterate, derivatives and solve state: copy its workspace in and go on
+              const WsStrided src = WsStrided::of(const_cast<double*>(tslab), L.total, tlist[e]);
+              for (int i = gg.lane; i < L.total; i += GL) ph_cp_async8(&ws[i], &src[i]);
+              ph_cp_async_wait();
+              gg.sync();
+              state = Phase<Model, WS, 1>::running(L, ws) ? RS_RUN : RS_EMPTY;
+              if (state == RS_RUN) {
+                const long b = (long)ws[L.st + 15];
+                if (!R::PhG::pre_body(P, L, ws, io, b, tab, gg, io.ns ? ph_globaltimer() : 0)) state = RS_EMPTY;
+              }
+            } else {
+              const long b = a.index ? (long)a.index[e] : (long)e;
+              R::load_body(P, L, ws, io, b, tab, gg, io.ns ? ph_globaltimer() : 0);
+              state = RS_NEW;
+            }
           } else {
             state = RS_DONE;
           }
