@@ -37,7 +37,6 @@ import math
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -380,27 +379,39 @@ CONFIGS = {c.key: c for c in (C1, C2, C3, C4, C4F, C5)}
 
 
 # =====================================================================================================================
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region: ONE background `nvidia-smi -lms 50` process
+    (the profiling recipe's clocks line), started before the timed region and stopped after it."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.proc, self.rows, self.stop_flag = index, None, [], False
 
-    def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 7:
-                    self.rows.append(f)
-            except Exception:
-                pass
-            time.sleep(0.1)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return
+        time.sleep(0.25)                      # at least one sample after short regions
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) >= 7:
+                self.rows.append(f)
+        self.proc = None
 
     def summary(self):
         if not self.rows:
@@ -519,7 +530,7 @@ def measure(wl, args, world, rank, dev, gather_mode, steps, warmup, sampler=None
     if world > 1:
         dist.barrier()
     if sampler is not None:
-        sampler.stop_flag = True
+        sampler.stop()
     launches = wl.solver.kernel_count() - launches0
     flush_ms = sum(a.elapsed_time(b) for a, b in fev)
     t_ms = t_start.elapsed_time(t_end) - flush_ms
@@ -623,7 +634,7 @@ def main():
 
     wl = CONFIGS[args.config](batch=args.batch, rank=rank)
     wl.setup(mv, dev, args.layout)
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if rank == 0 and not os.environ.get("BENCH_NO_SAMPLER") else None
     m = measure(wl, args, world, rank, dev, args.gather, args.steps, args.warmup, sampler, with_latency=True)
     assert m["ok"], "solver failures in the benchmark batch"
 
@@ -714,7 +725,7 @@ def main():
             "parallelism": "problem-index sharding x%d, NCCL all-gather of results + stats (%s)" % (world, args.gather)}),
         "e2e": m["e2e"],
         "gpu_launches": m["launches"],
-        "clocks": sampler.summary(),
+        "clocks": sampler.summary() if sampler is not None else None,
         "roofline": roofline_of(wl, m, peak_tf, hbm_peak, hbm_src),
         "cpu_baseline": cpu,
         "mean_ipm_iters": m["iters_sum"] / m["n_solves"],
