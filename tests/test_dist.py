@@ -3,6 +3,7 @@ import os
 import socket
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -49,3 +50,53 @@ def test_gather_and_stats_world_size_2(tmp_path):
     assert torch.equal(r["got"], full)                       # bit-for-bit the single-process result
     assert r["stats"]["problems"] == B and r["stats"]["succeeded"] == B
     assert r["stats"]["iters_sum"] == 5 * 10 + 6 * 11 and r["stats"]["iters_max"] == 11
+
+
+# ---- T11 on real GPUs: NCCL gather of SOLVER output == the shards solved alone, bit for bit ----------------------
+def _gpu_worker(rank, world, port, B, out):
+    import mpc_verde_b200 as mv
+    from mpc_verde_b200 import problems
+    from tests import common
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    prob = problems.unicycle_multiple_shooting()
+    solver = mv.nlpsol("solver", "ipopt", prob, {"ipopt": {"max_iter": 2000, "print_level": 0}})
+    sp = solver.spec
+    x0s, p = common.unicycle_batch(B)
+    lbx, ubx = problems.unicycle_bounds(sp, x_box=20.0)
+    w0 = problems.cold_start(sp, x0s)
+    lo, hi = mdist.shard_range(B, rank, world)
+    sol = solver(x0=torch.as_tensor(w0[lo:hi]).to(dev), lbx=lbx, ubx=ubx, p=torch.as_tensor(p[lo:hi]).to(dev), outputs=("x", "f"))
+    st, it = solver._last
+    xs, fs = mdist.gather_rows(sol["x"]), mdist.gather_rows(sol["f"])
+    stats = mdist.reduce_stats(st, it)
+    if rank == 0:
+        # every shard once more, alone on this GPU: the multi-GPU plumbing must not change one bit
+        alone = []
+        for r in range(world):
+            a, b = mdist.shard_range(B, r, world)
+            s1 = solver(x0=torch.as_tensor(w0[a:b]).to(dev), lbx=lbx, ubx=ubx, p=torch.as_tensor(p[a:b]).to(dev), outputs=("x", "f"))
+            alone.append((s1["x"].clone(), s1["f"].clone(), solver._last[1].clone()))
+        torch.save({"xs": xs.cpu(), "fs": fs.cpu(), "stats": stats,
+                    "x1": torch.cat([a[0] for a in alone]).cpu(), "f1": torch.cat([a[1] for a in alone]).cpu(),
+                    "iters1": int(sum(int(a[2].sum()) for a in alone))}, out)
+    dist.destroy_process_group()
+
+
+@pytest.mark.gpu
+def test_multi_gpu_gather_of_solver_output_is_bit_identical(tmp_path):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run under `gpurun --gpus 2`)")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    B = 20000
+    out = str(tmp_path / "r0.pt")
+    mp.spawn(_gpu_worker, args=(2, port, B, out), nprocs=2, join=True)
+    r = torch.load(out)
+    assert r["xs"].shape == (B, 53) and torch.equal(r["xs"], r["x1"]) and torch.equal(r["fs"], r["f1"])
+    assert r["stats"]["problems"] == B and r["stats"]["succeeded"] == B and r["stats"]["iters_sum"] == r["iters1"]
