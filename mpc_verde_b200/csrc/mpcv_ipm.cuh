@@ -59,6 +59,8 @@ struct Grp {
     return v;
   }
   MPCV_D int bcast(int v) const { return LANES > 1 ? __shfl_sync(mask, v, 0, LANES) : v; }
+  // true when `ok` holds on every lane of the group (one vote instead of a shuffle tree)
+  MPCV_D bool all(bool ok) const { return LANES > 1 ? (__ballot_sync(mask, ok) & mask) == mask : ok; }
 #else
   explicit Grp(int) : lane(0), mask(1u) { static_assert(LANES == 1, "host harness is single-lane"); }
   void sync() const {}
@@ -66,6 +68,7 @@ struct Grp {
   double max(double v) const { return v; }
   double min(double v) const { return v; }
   int bcast(int v) const { return v; }
+  bool all(bool ok) const { return ok; }
 #endif
 };
 
@@ -906,7 +909,7 @@ struct Ipm {
           }
         }
       }
-      ok = (LANES > 1) ? (g.min(okl ? 1.0 : 0.0) > 0.0 ? 1 : 0) : okl;
+      ok = g.all(okl != 0) ? 1 : 0;
       g.sync();
       if (!ok) break;
       // ---- step B: the entries of P_k = Qxx + A'PA + G'K and of p_k = r_x + A' Pd + K' g ----
@@ -1320,6 +1323,7 @@ struct Ipm {
   }
   // forward sweep: dx_0 = c_0, du = K dx + kff, dx+ = A dx + B du + c+, lam+_k = P_k dx_k + p_k
   MPCV_D void riccati_forward(int coff) const {
+    if (LANES > 1) { riccati_forward_lanes(coff); return; }
     if (g.lane == 0) {
       double dx[NX];
 #pragma unroll
@@ -1364,6 +1368,49 @@ struct Ipm {
 #pragma unroll
         for (int i = 0; i < NX; ++i) dx[i] = dn[i];
       }
+    }
+    g.sync();
+  }
+  // Lane groups: only the state recursion dx_{k+1} = A dx + B (K dx + kff) + c is a chain; it runs on lane 0 with
+  // nothing else on it.  The multipliers lam+_k = P_k dx_k + p_k are independent outputs once the dx are known and
+  // are computed by all lanes afterwards.  Same expressions as the single-lane form: bit-identical.
+  MPCV_D void riccati_forward_lanes(int coff) const {
+    if (g.lane == 0) {
+      double dx[NX];
+#pragma unroll
+      for (int i = 0; i < NX; ++i) { dx[i] = (coff >= 0) ? ws[coff + i] : 0.0; ws[L.d + ix(0, i)] = dx[i]; }
+      for (int k = 0; k < N; ++k) {
+        const WS ab = ws.view(L.ab + k * NAB), ric = ws.view(L.ric + k * NRIC);
+        double du[NU], dn[NX];
+#pragma unroll
+        for (int i = 0; i < NU; ++i) {
+          double v = ric[NU * NX + i];
+#pragma unroll
+          for (int j = 0; j < NX; ++j) v += ric[i * NX + j] * dx[j];
+          du[i] = v;
+          ws[L.d + iu(k, i)] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) {
+          double v = (coff >= 0) ? ws[coff + (k + 1) * NX + i] : 0.0;
+#pragma unroll
+          for (int j = 0; j < NX; ++j) v += ab[i * NX + j] * dx[j];
+#pragma unroll
+          for (int j = 0; j < NU; ++j) v += ab[NX * NX + i * NU + j] * du[j];
+          dn[i] = v;
+        }
+#pragma unroll
+        for (int i = 0; i < NX; ++i) { dx[i] = dn[i]; ws[L.d + ix(k + 1, i)] = dn[i]; }
+      }
+    }
+    g.sync();
+    for (int it = g.lane; it < (N + 1) * NX; it += LANES) {
+      const int k = it / NX, i = it - k * NX;
+      const WS pk = ws.view(L.pp + k * NPP);
+      double v = pk[NPX + i];
+#pragma unroll
+      for (int j = 0; j < NX; ++j) v += pk[j <= i ? tri(i, j) : tri(j, i)] * ws[L.d + ix(k, j)];
+      ws[L.lamp + it] = v;
     }
     g.sync();
   }

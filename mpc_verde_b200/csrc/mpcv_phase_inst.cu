@@ -302,7 +302,10 @@ static int res_prepare(mpcv_handle* h) {
 // the stragglers of the sweeps finish in the resident kernel when an SM holds enough problems (else ph_tail_kernel)
 constexpr int kResidentMinSlots = 8;
 static bool res_tail_usable(const mpcv_handle* h) {
-  if (h->knobs.res_tail == 0) return false;
+  // opt-in (MPCV_RES_TAIL=1): measured on C2 it is level with ph_tail_kernel on an average batch (15.5 vs 15.9 ms) and
+  // worse on a batch with a 119-iteration straggler (19.2 vs 18.2 ms): a slot that shares its CTA turns over in
+  // ~100 us per iteration, a lone warp of ph_tail_kernel in ~30 us
+  if (h->knobs.res_tail != 1) return false;
   return res_slots_per_sm(h) >= kResidentMinSlots;
 }
 // layout of this call: AUTO = the resident kernel for batches below the crossover with the slab pipeline
