@@ -464,7 +464,11 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config_block(wl, 1, {"sample": sample}),
+        # the same keys and values as the GPU arm's line for this configuration; what the CPU arm actually ran per
+        # step (a bounded sample of the workload) is said in cpu_baseline.sample
+        "config": config_block(wl, args.gpus, {
+            "l2": "flushed between steps (256 MB write)", "layout": "auto",
+            "parallelism": "problem-index sharding x%d, NCCL all-gather of results + stats (inline)" % args.gpus}),
         "cpu_baseline": {"value": value, "unit": "solves/s", "cores": threads, "kind": "port",
                          "sample": "%s x %d steps, %d host threads (CasADi/IPOPT not installable offline; oracle port "
                                    "of IPOPT's algorithm)" % (sample, args.steps, threads)},
