@@ -72,7 +72,7 @@ def test_c4_tracker_closed_loops_full_size(env, key):
         err = np.hypot(*(st[:, :, :2] - refs).transpose(2, 0, 1))
         assert err[:, 20:].max() < 0.5                                     # the tracker stays on the lane-change path
     else:
-        assert np.abs(st[:, :, 3]).max() <= 0.384 + 1e-9                   # |delta| <= 0.384 (box on the delta state)
+        assert np.abs(st[:, :, 3]).max() <= 0.384 + 1e-7                   # |delta| <= 0.384: a box on the delta state of the NLP (relaxed by 1e-8 inside the solve, constr_viol_tol on the defect)
 
 
 def test_c5_dynamic_bicycle_ltv_full_size(env):
