@@ -204,6 +204,7 @@ struct Ipm {
   // the filter entries themselves stay in the workspace (state slots 16.., 24..): arrays indexed by a run-time
   // nfil would live in local memory and be copied through it at every hand-over between phases
   int nfil, iter;
+  bool resto_sigma = false;   // identity-Hessian factorisations add the diagonal in L.sig (restoration: affine scaling)
   int acc_count;        // consecutive iterates within the acceptable tolerances
   double f_last;        // objective at the previous convergence test
   MPCV_D double& fil_phi(int q) const { return ws[L.st + 16 + q]; }
@@ -212,15 +213,15 @@ struct Ipm {
   double ls_alpha_max, ls_theta, ls_gBD, ls_phi;
   // barrier log-sum of the current iterate = log-sum of the trial point accepted last (same slacks): reused by
   // direction_post instead of ~2 logs per bounded variable
-  double lg_curr;
+  double lg_curr, dmp_curr;   // (and the one-sided slack sum of the damping term)
   bool lg_valid;
-  mutable double lg_trial;   // log-sum of the most recent trial evaluation
+  mutable double lg_trial, dmp_trial;   // log-sum / slack sum of the most recent trial evaluation
 
   MPCV_D Ipm(const Params& p, const Layout& l, WS w, Grp<LANES> grp, const double* lb, const double* ub,
              const BndEntry* tab = nullptr)
       : P(p), L(l), ws(w), g(grp), lbx(lb), ubx(ub), btab(tab), N(l.N), ps_base(l.par + NX + Model::NPG),
         df(1.0), mu(0.1), tau(0.99), f_curr(0), theta_max(-1.0), theta_min(-1.0), delta_w_last(0.0), nfil(0),
-        iter(0), acc_count(0), f_last(-1e50), ls_alpha_max(1.0), ls_theta(0.0), ls_gBD(0.0), ls_phi(0.0), lg_curr(0.0), lg_valid(false), lg_trial(0.0) {}
+        iter(0), acc_count(0), f_last(-1e50), ls_alpha_max(1.0), ls_theta(0.0), ls_gBD(0.0), ls_phi(0.0), lg_curr(0.0), dmp_curr(0.0), lg_valid(false), lg_trial(0.0), dmp_trial(0.0) {}
 
   // ---- state hand-over between phase kernels ---------------------------------------------------
   MPCV_D void save_state(int status) const {
@@ -231,7 +232,7 @@ struct Ipm {
     ws[o + 7] = (double)nfil; ws[o + 8] = (double)iter; ws[o + 9] = (double)status;
     ws[o + 10] = ls_alpha_max; ws[o + 11] = ls_theta; ws[o + 12] = ls_gBD; ws[o + 13] = ls_phi;
     ws[o + 35] = lg_curr; ws[o + 36] = lg_valid ? 1.0 : 0.0;
-    ws[o + 37] = (double)acc_count; ws[o + 38] = f_last;
+    ws[o + 37] = (double)acc_count; ws[o + 38] = f_last; ws[o + 39] = dmp_curr;
   }
   MPCV_D int load_state() {
     const int o = L.st;
@@ -240,7 +241,7 @@ struct Ipm {
     nfil = (int)ws[o + 7]; iter = (int)ws[o + 8];
     ls_alpha_max = ws[o + 10]; ls_theta = ws[o + 11]; ls_gBD = ws[o + 12]; ls_phi = ws[o + 13];
     lg_curr = ws[o + 35]; lg_valid = ws[o + 36] != 0.0;
-    acc_count = (int)ws[o + 37]; f_last = ws[o + 38];
+    acc_count = (int)ws[o + 37]; f_last = ws[o + 38]; dmp_curr = ws[o + 39];
     return (int)ws[o + 9];
   }
 
@@ -485,13 +486,25 @@ struct Ipm {
   // quarter of the instructions of the line-search kernels.
   struct LogSum {
     double lg = 0.0, prod = 1.0;
+    double damp = 0.0;      // sum of the slacks of ONE-sided bounds (IPOPT's linear damping term kappa_d mu (x - x_L))
     int cnt = 0;
     MPCV_D void add(double s) {
       prod *= s;
       if (++cnt == 8) { lg += log(prod); prod = 1.0; cnt = 0; }
     }
+    // slacks of variable i with bounds b at value v; returns false when a slack is not positive
+    template <class B>
+    MPCV_D bool add_var(const B& b, double v) {
+      bool ok = true;
+      if (b.hasl) { const double s = v - b.lo; if (!(s > 0.0)) ok = false; add(s); if (!b.hasu) damp += s; }
+      if (b.hasu) { const double s = b.hi - v; if (!(s > 0.0)) ok = false; add(s); if (!b.hasl) damp += s; }
+      return ok;
+    }
     MPCV_D double value() const { return cnt ? lg + log(prod) : lg; }
   };
+  // kappa_d of IPOPT (one-sided bounds only: none of the reference scripts has one; two-sided boxes are undamped)
+  static constexpr double kKappaD = 1e-4;
+  MPCV_D double phi_of(double f, double lg, double damp) const { return f - mu * lg + kKappaD * mu * damp; }
 
   // ---- objective / constraint violation / barrier at  w + alpha * (vector at doff) -------------
   // returns scaled f; theta = ||c||_1; barrier log terms; optionally stores the residuals in ct
@@ -540,9 +553,7 @@ struct Ipm {
     for (int i = g.lane; i < L.n; i += LANES) {
       const Bnd b = bnd(i);
       if (b.hasl || b.hasu) {
-        const double v = ws[L.w + i] + alpha * ws[doff + i];
-        if (b.hasl) { const double s = v - b.lo; if (!(s > 0.0)) bad = true; ls.add(s); }
-        if (b.hasu) { const double s = b.hi - v; if (!(s > 0.0)) bad = true; ls.add(s); }
+        if (!ls.add_var(b, ws[L.w + i] + alpha * ws[doff + i])) bad = true;
       }
     }
     logpart = ls.value();
@@ -550,10 +561,11 @@ struct Ipm {
     const double th = g.sum(thpart);
     double lg = g.sum(logpart);
     lg_trial = lg;
+    dmp_trial = g.sum(ls.damp);
     const bool anybad = g.max(bad ? 1.0 : 0.0) > 0.0;
     *f_out = f;
     *theta_out = th;
-    *phi_out = anybad ? INFINITY : f - mu * lg;
+    *phi_out = anybad ? INFINITY : phi_of(f, lg, dmp_trial);
     if (store_ct) g.sync();
   }
 
@@ -582,19 +594,18 @@ struct Ipm {
     lane_loop(L.n, [&](int i) { return V2{ws[L.w + i], ws[doff + i]}; }, [&](int i, const V2& q) {
       const Bnd b = bnd(i);
       if (b.hasl || b.hasu) {
-        const double v = q.a + alpha * q.b;
-        if (b.hasl) { const double s = v - b.lo; if (!(s > 0.0)) bad = true; ls.add(s); }
-        if (b.hasu) { const double s = b.hi - v; if (!(s > 0.0)) bad = true; ls.add(s); }
+        if (!ls.add_var(b, q.a + alpha * q.b)) bad = true;
       }
     });
     logpart = ls.value();
     const double f = sum_stage_costs();
     const double lg = g.sum(logpart);
     lg_trial = lg;
+    dmp_trial = g.sum(ls.damp);
     const bool anybad = g.max(bad ? 1.0 : 0.0) > 0.0;
     *f_out = f;
     *theta_out = g.sum(thpart);
-    *phi_out = anybad ? INFINITY : f - mu * lg;
+    *phi_out = anybad ? INFINITY : phi_of(f, lg, dmp_trial);
     g.sync();
   }
 
@@ -678,6 +689,7 @@ struct Ipm {
     // one reciprocal per bound serves Sigma = z / s and the barrier gradient mu / s
     if (b.hasl) { const double inv = 1.0 / (ws[L.w + i] - b.lo); s += ws[L.zl + i] * inv; ri -= mu * inv; }
     if (b.hasu) { const double inv = 1.0 / (b.hi - ws[L.w + i]); s += ws[L.zu + i] * inv; ri += mu * inv; }
+    if (b.hasl != b.hasu) ri += b.hasl ? kKappaD * mu : -kKappaD * mu;
     *sg = s; *r = ri;
   }
   MPCV_D void prepare_barrier() const {
@@ -688,6 +700,7 @@ struct Ipm {
       // one reciprocal per bound serves Sigma = z / s and the barrier gradient mu / s
       if (b.hasl) { const double inv = 1.0 / (v.b - b.lo); s += v.c * inv; ri -= mu * inv; }
       if (b.hasu) { const double inv = 1.0 / (b.hi - v.b); s += v.d * inv; ri += mu * inv; }
+      if (b.hasl != b.hasu) ri += b.hasl ? kKappaD * mu : -kKappaD * mu;      // linear damping of one-sided bounds
       ws[L.sig + i] = s;
       ws[L.rb + i] = ri;
     });
@@ -730,7 +743,7 @@ struct Ipm {
 #pragma unroll
       for (int i = 0; i < NW; ++i) s.W[i] = 0.0;
 #pragma unroll
-      for (int i = 0; i < NZ; ++i) { s.W[tri(i, i)] = 1.0; s.sg[i] = 0.0; }
+      for (int i = 0; i < NZ; ++i) { s.W[tri(i, i)] = 1.0; s.sg[i] = resto_sigma ? ws[L.sig + k * NZ + i] : 0.0; }
     } else {
 #pragma unroll
       for (int i = 0; i < NW; ++i) s.W[i] = ws[L.hw + k * NW + i];
@@ -777,7 +790,7 @@ struct Ipm {
           double v = 0.0;
           if (r == c) {
             double sg = 0.0, rr;
-            if (!identity) sigma_r(ix(N, r), &sg, &rr);
+            if (!identity || resto_sigma) sigma_r(ix(N, r), &sg, &rr);
             v = (identity ? 1.0 : 0.0) + sg + dw;
           }
           pn[i] = v;
@@ -820,7 +833,7 @@ struct Ipm {
 #pragma unroll
           for (int j = 0; j <= i; ++j) {
             double v = identity ? (i == j ? 1.0 : 0.0) : hw[tri(NX + i, NX + j)];
-            if (!identity && i == j) v += sgv[NX + i] + dw;
+            if ((!identity || resto_sigma) && i == j) v += sgv[NX + i] + dw;
 #pragma unroll
             for (int l = 0; l < NX; ++l) v += B[l * NU + i] * PB[l * NU + j];
             F[i * NU + j] = v;
@@ -923,7 +936,7 @@ struct Ipm {
         double v;
         if (mat) {
           v = identity ? (i == j ? 1.0 : 0.0) : hw[it];
-          if (!identity && i == j) v += sgv[i] + dw;
+          if ((!identity || resto_sigma) && i == j) v += sgv[i] + dw;
         } else {
           v = rvar(rmode, ix(k, i));
         }
@@ -960,7 +973,7 @@ struct Ipm {
 #pragma unroll
       for (int i = 0; i < NX; ++i) {
         double sg = 0.0, r;
-        if (!identity) sigma_r(ix(N, i), &sg, &r);
+        if (!identity || resto_sigma) sigma_r(ix(N, i), &sg, &r);
         Pm[i * NX + i] = (identity ? 1.0 : 0.0) + sg + dw;
       }
       if (STORE) store_P(N, Pm);
@@ -975,7 +988,7 @@ struct Ipm {
         for (int i = 0; i < NX * NU; ++i) B[i] = cur.B[i];
 #pragma unroll
         for (int i = 0; i < NW; ++i) W[i] = cur.W[i];
-        if (!identity) {
+        if (!identity || resto_sigma) {
 #pragma unroll
           for (int i = 0; i < NZ; ++i) W[tri(i, i)] += cur.sg[i] + dw;
         }
@@ -1173,6 +1186,7 @@ struct Ipm {
   struct BwdIn { double P[NPX], c[NX], A[NX * NX], B[NX * NU], K[NU * NX], F[NF], ru[NU], rx[NX]; };
   struct FwdIn { double P[NPX], p[NX], K[NU * NX], kff[NU], A[NX * NX], B[NX * NU], c[NX]; };
   MPCV_D double rvar(int rmode, int v) const {
+    if (rmode == 2) return 0.0;                                        // feasibility step: minimise |d|^2 only
     if (rmode == 1) return ws[L.grad + v] - ws[L.zl + v] + ws[L.zu + v];
     return ws[L.rb + v];
   }
@@ -1729,16 +1743,14 @@ struct Ipm {
     lane_loop(L.n, [&](int i) { return V3{ws[L.rb + i], ws[L.d + i], ws[L.w + i]}; }, [&](int i, const V3& v) {
       const Bnd b = bnd(i);
       if (!b.fixed) gBD += v.a * v.b;
-      if (need_lg) {
-        if (b.hasl) ls.add(v.c - b.lo);
-        if (b.hasu) ls.add(b.hi - v.c);
-      }
+      if (need_lg) ls.add_var(b, v.c);
     });
     theta = g.sum(theta); gBD = g.sum(gBD);
     lg = need_lg ? g.sum(ls.value()) : lg_curr;
+    const double dmp = need_lg ? g.sum(ls.damp) : dmp_curr;
     ls_theta = theta;
     ls_gBD = gBD;
-    ls_phi = f_curr - mu * lg;
+    ls_phi = phi_of(f_curr, lg, dmp);
     if (theta_max < 0.0) { theta_max = 1e4 * fmax(1.0, theta); theta_min = 1e-4 * fmax(1.0, theta); }
   }
   MPCV_D int compute_direction() { return direction_first() ? 0 : direction_retry(); }
@@ -1814,6 +1826,7 @@ struct Ipm {
       lane_loop(L.m, [&](int i) { return V2{ws[L.lam + i], ws[L.lamp + i]}; },
                 [&](int i, const V2& v) { ws[L.lam + i] = v.a + alpha * (v.b - v.a); });
     lg_curr = lg_trial;          // the accepting trial evaluation was the last one
+    dmp_curr = dmp_trial;
     lg_valid = true;
     g.sync();
     sync_blocked();
@@ -1885,8 +1898,90 @@ struct Ipm {
       alpha *= 0.5;
       ++nsteps;
     }
-    if (!accepted) return MPCV_RESTORATION_FAILED;
+    if (!accepted) return SINGLE ? (int)MPCV_RESTORATION_FAILED : restoration();
     ls_accept_step(alpha, alpha_test, phi_acc, pw);
+    return 0;
+  }
+
+  // ---- feasibility restoration ----------------------------------------------------------------------------
+  // IPOPT switches to its restoration phase when the line search cannot find an acceptable step (alpha < alpha_min):
+  // it leaves the current point in the filter, reduces the constraint violation until the point is acceptable to the
+  // filter again with theta <= kappa_resto theta_R (kappa_resto = 0.9), resets the equality multipliers
+  // (constr_mult_reset_threshold = 0) and resumes.  IPOPT minimises rho |c|_1 + zeta/2 |D_R (x - x_R)|^2 by another
+  // interior-point solve; here the phase is a damped Gauss-Newton iteration on theta: the scaled minimum-norm step
+  // d = argmin |d|^2 + sum_i (d_i / s_i)^2  s.t.  J d = -c  (the identity-Hessian Riccati system the multiplier
+  // initialisation uses, plus an affine scaling by the bound slacks s_i) with the fraction-to-the-boundary rule and an
+  // Armijo test on theta.  Every restoration step counts as an iteration, like
+  // IPOPT's.  Returns 0 with the new iterate in place (derivatives evaluated), or MPCV_RESTORATION_FAILED.
+  static constexpr int kRestoMaxIter = 40, kRestoMaxBacktrack = 30;
+  MPCV_D bool filter_ok(double phi_t, double theta_t) const {
+    if (!(phi_t < INFINITY) || !(theta_t < INFINITY)) return false;
+    if (theta_max > 0.0 && theta_t > theta_max) return false;
+    for (int q = 0; q < nfil; ++q) {
+      const double fp = fil_phi(q), ft = fil_th(q);
+      if (!(compare_le(phi_t, fp, fp) || compare_le(theta_t, ft, ft))) return false;
+    }
+    return true;
+  }
+  MPCV_DN int restoration() {
+    const double theta_R = ls_theta, phi_R = ls_phi;
+    if (!(theta_R > P.tol)) return MPCV_RESTORATION_FAILED;          // (almost) feasible: nothing to restore
+    // the point we leave goes into the filter
+    if (nfil < FILTER_MAX) {
+      if (g.lane == 0) { fil_phi(nfil) = phi_R - 1e-8 * theta_R; fil_th(nfil) = (1.0 - 1e-5) * theta_R; }
+      ++nfil;
+    } else if (g.lane == 0) {
+      for (int q = 1; q < FILTER_MAX; ++q) { fil_phi(q - 1) = fil_phi(q); fil_th(q - 1) = fil_th(q); }
+      fil_phi(FILTER_MAX - 1) = phi_R - 1e-8 * theta_R; fil_th(FILTER_MAX - 1) = (1.0 - 1e-5) * theta_R;
+    }
+    g.sync();
+    double theta = theta_R;
+    bool done = false;
+    for (int r = 0; r < kRestoMaxIter && !done; ++r) {
+      // affine scaling: the step is measured in |d|^2 + sum_i (d_i / s_i)^2 over the bound slacks s_i, so that a variable
+      // sitting at a bound hardly moves and the fraction-to-the-boundary rule does not choke the step
+      for (int i = g.lane; i < L.n; i += LANES) {
+        const Bnd b = bnd(i);
+        double sg = 0.0;
+        if (b.hasl) { const double sl = ws[L.w + i] - b.lo; sg += 1.0 / (sl * sl); }
+        if (b.hasu) { const double su = b.hi - ws[L.w + i]; sg += 1.0 / (su * su); }
+        ws[L.sig + i] = sg;
+      }
+      g.sync();
+      resto_sigma = true;
+      const bool fok = riccati_factor(0.0, true);
+      resto_sigma = false;
+      if (!fok) return MPCV_RESTORATION_FAILED;
+      riccati_solve(2, L.c);
+      double alpha = ftb_primal();
+      double f_t = 0.0, theta_t = 0.0, phi_t = 0.0;
+      bool found = false;
+      for (int j = 0; j < kRestoMaxBacktrack && !found; ++j) {
+        eval_trial(alpha, L.d, false, &f_t, &theta_t, &phi_t);
+        if (phi_t < INFINITY && theta_t <= (1.0 - 1e-4 * alpha) * theta) found = true;
+        else alpha *= 0.5;
+      }
+      if (!found) return MPCV_RESTORATION_FAILED;
+      for (int i = g.lane; i < L.n; i += LANES) ws[L.w + i] = ws[L.w + i] + alpha * ws[L.d + i];
+      g.sync();
+      sync_blocked();
+      ++iter;
+      theta = theta_t;
+      eval_derivatives(true);
+      if (theta_t <= 0.9 * theta_R && filter_ok(phi_t, theta_t)) done = true;
+      if (iter >= P.max_iter) break;
+    }
+    if (!done) return MPCV_RESTORATION_FAILED;
+    // back to the regular algorithm: equality multipliers reset, bound multipliers kept inside their safeguard band
+    for (int i = g.lane; i < L.m; i += LANES) ws[L.lam + i] = 0.0;
+    for (int i = g.lane; i < L.n; i += LANES) {
+      const Bnd b = bnd(i);
+      if (b.hasl) ws[L.zl + i] = clamp_z(ws[L.zl + i], ws[L.w + i] - b.lo);
+      if (b.hasu) ws[L.zu + i] = clamp_z(ws[L.zu + i], b.hi - ws[L.w + i]);
+    }
+    g.sync();
+    eval_derivatives(true);      // the Hessian of the Lagrangian depends on the multipliers
+    lg_valid = false;
     return 0;
   }
 
@@ -1960,19 +2055,18 @@ struct Ipm {
     for (int i = g.lane; i < L.n; i += LANES) {
       const Bnd b = bnd(i);
       if (b.hasl || b.hasu) {
-        const double v = ws[L.w + i] + alpha_soc * ws[L.d + i];
-        if (b.hasl) { const double s = v - b.lo; if (!(s > 0.0)) bad = true; ls.add(s); }
-        if (b.hasu) { const double s = b.hi - v; if (!(s > 0.0)) bad = true; ls.add(s); }
+        if (!ls.add_var(b, ws[L.w + i] + alpha_soc * ws[L.d + i])) bad = true;
       }
     }
     logpart = ls.value();
     const double f = df * g.sum(fpart);
     const double lg = g.sum(logpart);
     lg_trial = lg;
+    dmp_trial = g.sum(ls.damp);
     const bool anybad = g.max(bad ? 1.0 : 0.0) > 0.0;
     *f_out = f;
     *theta_out = g.sum(thpart);
-    *phi_out = anybad ? INFINITY : f - mu * lg;
+    *phi_out = anybad ? INFINITY : phi_of(f, lg, dmp_trial);
     g.sync();
   }
 

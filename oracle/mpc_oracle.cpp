@@ -30,6 +30,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <cstdio>
 #include <cstdint>
 #include <cstring>
 #include <limits>
@@ -427,6 +429,9 @@ struct IpmOptions {
   double tau_min = 0.99;          // tau_min
   double s_max = 100.0;           // s_max
   double kappa_sigma = 1e10;      // kappa_sigma
+  double kappa_d = 1e-4;          // kappa_d (damping of one-sided bounds)
+  double kappa_resto = 0.9;       // required_infeasibility_reduction
+  int resto_max_iter = 40, resto_max_backtrack = 30;
   double constr_mult_init_max = 1e3;
   // filter line search
   double theta_max_fact = 1e4, theta_min_fact = 1e-4, eta_phi = 1e-8, delta = 1.0, s_phi = 2.3,
@@ -541,6 +546,9 @@ class Ipm {
     for (int i = 0; i < n; ++i) {
       if (hasl[i]) phi -= mu * std::log(v[i] - lb[i]);
       if (hasu[i]) phi -= mu * std::log(ub[i] - v[i]);
+      // linear damping of one-sided bounds (kappa_d, Waechter & Biegler 2006, sec. 3.7)
+      if (hasl[i] && !hasu[i]) phi += opt.kappa_d * mu * (v[i] - lb[i]);
+      if (hasu[i] && !hasl[i]) phi += opt.kappa_d * mu * (ub[i] - v[i]);
     }
     return phi;
   }
@@ -896,6 +904,8 @@ class Ipm {
         double sg = 0, ri = grad[i];
         if (hasl[i]) { double sl = w[i] - lb[i]; sg += zl[i] / sl; ri -= mu / sl; }
         if (hasu[i]) { double su = ub[i] - w[i]; sg += zu[i] / su; ri += mu / su; }
+        if (hasl[i] && !hasu[i]) ri += opt.kappa_d * mu;
+        if (hasu[i] && !hasl[i]) ri -= opt.kappa_d * mu;
         sigma[i] = sg; r[i] = ri;
       }
       double dw = 0.0;
@@ -1013,7 +1023,61 @@ class Ipm {
         ++nsteps;
         ++st.n_backtracks;
       }
-      if (!accepted) { st.status = MPCV_RESTORATION_FAILED; break; }   // restoration phase not restated
+      if (!accepted) {
+        // --- feasibility restoration (IPOPT: IpRestoMinC_1Nrm; here the simplified phase DESIGN.md states): the point
+        // we leave enters the filter; damped minimum-norm Gauss-Newton steps on theta = |c|_1 until the point is
+        // acceptable to the filter with theta <= kappa_resto theta_R; equality multipliers reset to zero ---
+        bool restored = false;
+        int n_resto = 0;
+        const bool dbg = getenv("MPCO_DEBUG_RESTO") != nullptr;
+        if (dbg) fprintf(stderr, "resto enter iter %d theta %.3e phi %.6e alpha_min %.3e gBD %.3e nfil %zu\n", iter, theta, phi, alpha_min, gBD, filter.size());
+        if (!single && theta > opt.tol) {
+          filter.emplace_back(phi - opt.gamma_phi * theta, (1.0 - opt.gamma_theta) * theta);
+          const double theta_R = theta;
+          double th = theta_R;
+          std::vector<double> sigR(n, 0.0), r0(n, 0.0), dr, lr, cc;
+          for (int it = 0; it < opt.resto_max_iter && !restored; ++it) {
+            // affine scaling: the step is measured in |d|^2 + sum_i (d_i / s_i)^2 over the bound slacks s_i, so that a
+            // variable sitting at a bound hardly moves and the fraction-to-the-boundary rule does not choke the step
+            for (int i = 0; i < n; ++i) {
+              double sg = 0.0;
+              if (hasl[i]) { double sl = w[i] - lb[i]; sg += 1.0 / (sl * sl); }
+              if (hasu[i]) { double su = ub[i] - w[i]; sg += 1.0 / (su * su); }
+              sigR[i] = sg;
+            }
+            if (!factor(sigR, 0.0, false)) break;
+            cc.assign(c.begin(), c.begin() + m);
+            backsolve(r0, cc, dr, lr);
+            double a = ftb_primal(dr), phi_t = 0, theta_t = 0;
+            bool found = false;
+            for (int j = 0; j < opt.resto_max_backtrack && !found; ++j) {
+              trial(dr, a, phi_t, theta_t);
+              if (std::isfinite(phi_t) && theta_t <= (1.0 - 1e-4 * a) * th) found = true;
+              else a *= 0.5;
+            }
+            if (dbg) fprintf(stderr, "  resto it %d found %d a %.3e theta_t %.3e (th %.3e) phi_t %.6e\n", it, (int)found, a, theta_t, th, phi_t);
+            if (!found) break;
+            for (int i = 0; i < n; ++i) w[i] = wt[i];
+            ++n_resto;
+            th = theta_t;
+            eval_derivatives();
+            bool fok = std::isfinite(phi_t) && !(theta_max > 0 && theta_t > theta_max);
+            for (auto& fe : filter)
+              if (!(compare_le(phi_t, fe.first, fe.first) || compare_le(theta_t, fe.second, fe.second))) fok = false;
+            if (theta_t <= opt.kappa_resto * theta_R && fok) restored = true;
+            if (iter + n_resto >= opt.max_iter) break;
+          }
+        }
+        if (!restored) { st.status = MPCV_RESTORATION_FAILED; st.iters = iter + n_resto; break; }
+        std::fill(ocp.lam.begin(), ocp.lam.end(), 0.0);
+        for (int i = 0; i < n; ++i) {
+          if (hasl[i]) { double sl = w[i] - lb[i]; zl[i] = std::max(std::min(zl[i], opt.kappa_sigma * mu / sl), mu / (opt.kappa_sigma * sl)); }
+          if (hasu[i]) { double su = ub[i] - w[i]; zu[i] = std::max(std::min(zu[i], opt.kappa_sigma * mu / su), mu / (opt.kappa_sigma * su)); }
+        }
+        eval_derivatives();
+        iter += n_resto - 1;      // every restoration step counts as an iteration (the loop adds the last one)
+        continue;
+      }
       // filter augmentation (h-type step)
       {
         double phi_t, theta_t;

@@ -332,3 +332,51 @@ def test_calls_on_two_streams_through_one_handle_are_ordered(mv):
         again = solver(x0=w0, lbx=lbx, ubx=ubx, p=p, outputs=("x", "f"))["x"]
         torch.cuda.synchronize()
         assert torch.equal(again, x)
+
+
+# ---- feasibility restoration, one-sided-bound damping ---------------------------------------------------------------
+@pytest.mark.parametrize("layout", ["PHASED", "RESIDENT", "WARP", "THREAD"])
+def test_zeros_guess_batch_recovers_through_restoration(mv, layout):
+    """the scripts' w0 = 0 from a far-away x0 drives IPOPT into its restoration phase.  The batch
+    that ended with 7 of 512 `Restoration_Failed` in round 1 must now solve everywhere, in every layout, on the oracle's
+    iteration path (the restoration steps count as iterations)."""
+    import torch
+    prob = problems.unicycle_multiple_shooting()
+    sp = prob["spec"]
+    x0s, p = common.unicycle_batch(512, seed=77)
+    lbx, ubx = problems.unicycle_bounds(sp)
+    solver = _solver(mv, prob, layout=getattr(S, "LAYOUT_" + layout))
+    sol = solver(x0=None, lbx=lbx, ubx=ubx, p=torch.as_tensor(p).cuda())
+    st = solver.stats()
+    ref = O.solve(sp, None, lbx, ubx, p, nthreads=NCPU)
+    assert np.all(ref["status"] == 0)
+    assert np.all(st["status_code"] == 0), np.unique(st["status_code"], return_counts=True)
+    same = st["iter_count"] == ref["iters"]
+    assert same.mean() >= 0.97, same.mean()
+    assert np.abs(sol["x"].cpu().numpy()[same] - ref["x"][same]).max() <= 1e-8
+    assert np.abs(sol["f"].cpu().numpy()[same] - ref["f"][same]).max() <= 1e-8 * np.abs(ref["f"]).max()
+
+
+def test_one_sided_bounds_are_damped_like_the_oracle(mv):
+    """kappa_d: a variable with only one finite bound gets IPOPT's linear damping term in the barrier objective and
+    its gradient.  None of the scripts has such a bound; the C2 batch with v >= -1, w <= pi/4 only exercises it."""
+    import torch
+    prob = problems.unicycle_multiple_shooting()
+    sp = prob["spec"]
+    x0s, p = common.unicycle_batch(512)
+    lbx, ubx = problems.unicycle_bounds(sp, x_box=20.0)
+    lbx, ubx = np.array(lbx, dtype=float), np.array(ubx, dtype=float)
+    nz = sp.nx + sp.nu
+    for k in range(sp.N):
+        ubx[k * nz + sp.nx] = np.inf          # v: lower bound only
+        lbx[k * nz + sp.nx + 1] = -np.inf     # w: upper bound only
+    w0 = problems.cold_start(sp, x0s)
+    ref = O.solve(sp, w0, lbx, ubx, p, nthreads=NCPU)
+    for lay in (S.LAYOUT_PHASED, S.LAYOUT_RESIDENT):
+        solver = _solver(mv, prob, layout=lay)
+        sol = solver(x0=torch.as_tensor(w0).cuda(), lbx=lbx, ubx=ubx, p=torch.as_tensor(p).cuda())
+        st = solver.stats()
+        assert np.array_equal(st["status_code"], ref["status"])
+        same = (ref["status"] == 0) & (st["iter_count"] == ref["iters"])
+        assert same.mean() >= 0.98
+        assert np.abs(sol["x"].cpu().numpy()[same] - ref["x"][same]).max() <= 1e-9

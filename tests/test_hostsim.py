@@ -164,3 +164,28 @@ def test_frenet_bicycle_ipm_vs_oracle():
     assert np.abs(a["x"] - b["x"]).max() <= 1e-8
     assert np.abs(a["f"] - b["f"]).max() <= 1e-9 * (1 + np.abs(a["f"]).max())
     assert _same(b, c)
+
+
+def test_restoration_and_one_sided_damping_oracle_vs_device_headers():
+    """Round 2: feasibility restoration (the w0 = 0 batch of SURVEY Appendix E has no failure left) and the kappa_d
+    damping of one-sided bounds, oracle (null-space condensing) against the device headers (Riccati), both schedules."""
+    sp = S.unicycle_multiple_shooting()
+    x0s, p = common.unicycle_batch(160, seed=77)
+    lbx, ubx = problems.unicycle_bounds(sp)
+    a, b, c = O.solve(sp, None, lbx, ubx, p), H.solve(sp, None, lbx, ubx, p), H.solve(sp, None, lbx, ubx, p, phased=True)
+    assert np.all(a["status"] == 0) and np.all(b["status"] == 0)
+    assert a["iters"].max() > 40                                   # the restoration cases are in the sample
+    same = a["iters"] == b["iters"]
+    assert same.mean() > 0.95
+    assert np.abs(a["x"][same] - b["x"][same]).max() <= 1e-8
+    assert _same(b, c)
+    x0s, p = common.unicycle_batch(100)
+    lbx, ubx = (np.array(v, dtype=float) for v in problems.unicycle_bounds(sp, x_box=20.0))
+    nz = sp.nx + sp.nu
+    for k in range(sp.N):
+        ubx[k * nz + sp.nx] = np.inf
+        lbx[k * nz + sp.nx + 1] = -np.inf
+    w0 = problems.cold_start(sp, x0s)
+    a, b = O.solve(sp, w0, lbx, ubx, p), H.solve(sp, w0, lbx, ubx, p)
+    assert np.all(a["status"] == 0) and np.array_equal(a["iters"], b["iters"])
+    assert np.abs(a["x"] - b["x"]).max() <= 1e-9
