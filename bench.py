@@ -81,7 +81,7 @@ class Workload:
     # -- device side --
     def setup(self, mv, dev, layout=S.LAYOUT_AUTO):
         import torch
-        self.mv, self.dev, self.torch = mv, dev, torch
+        self.mv, self.dev, self.torch, self.layout = mv, dev, torch, layout
         self.solver = mv.nlpsol("solver", "ipopt", self.problem(), dict(OPTS, layout=layout))
         self.spec = self.solver.spec
         self._setup_inputs()
@@ -467,7 +467,8 @@ def run_reference(args):
         # the same keys and values as the GPU arm's line for this configuration; what the CPU arm actually ran per
         # step (a bounded sample of the workload) is said in cpu_baseline.sample
         "config": config_block(wl, args.gpus, {
-            "l2": "flushed between steps (256 MB write)", "layout": "auto",
+            "l2": "flushed between steps (256 MB write)", "batches_in_flight": 1 if wl.key == "c1" else max(1, args.inflight),
+            "layout": "auto",
             "parallelism": "problem-index sharding x%d, NCCL all-gather of results + stats (inline)" % args.gpus}),
         "cpu_baseline": {"value": value, "unit": "solves/s", "cores": threads, "kind": "port",
                          "sample": "%s x %d steps, %d host threads (CasADi/IPOPT not installable offline; oracle port "
@@ -489,78 +490,139 @@ def counted_flops_per_iter(key):
         return None
 
 
-def measure(wl, args, world, rank, dev, gather_mode, steps, warmup, sampler=None, with_latency=False):
+def measure(wl, args, world, rank, dev, gather_mode, steps, warmup, sampler=None, with_latency=False, inflight=1):
     """timed region of one workload: K steps, CUDA events on the launching stream, L2 flushed between steps, NCCL
-    gather of the results after every step; then the end-to-end leg through the public API from host buffers."""
+    gather of the results after every step; then the end-to-end leg through the public API from host buffers.
+
+    inflight = F > 1: the K steps alternate over F solver handles on F streams (batch k goes to handle k mod F), so
+    that the sparse end of one batch (late sweeps, straggler tail: a few warps busy) runs underneath the dense sweeps
+    of the next one.  Still exactly K solves of the full batch between the two synchronisation points; the serial
+    figure (one batch at a time, F = 1) is measured in the same run and reported beside it."""
+    from concurrent.futures import ThreadPoolExecutor
+
     import torch
     import torch.distributed as dist
     from mpc_verde_b200 import dist as mdist
 
-    flush = torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev)   # > 126 MB L2
+    F = max(1, int(inflight))
+    wls = [wl]
+    for _ in range(F - 1):
+        w = type(wl)(batch=wl.B, rank=wl.rank)
+        w.setup(wl.mv, dev, wl.layout)
+        wls.append(w)
+    main = torch.cuda.current_stream(dev)
+    streams = [main] if F == 1 else [torch.cuda.Stream(dev) for _ in wls]
+    flush = [torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev) for _ in streams]   # > 126 MB L2
 
-    def gather(outs):
+    def gather(w, outs):
         if world == 1 or gather_mode == "none":
             return None
         g = [mdist.gather_rows_equal(o.reshape(o.shape[0], -1)) for o in outs]
-        return g, mdist.reduce_stats_device(wl.status, wl.iters)
+        return g, mdist.reduce_stats_device(w.status, w.iters)
 
-    for _ in range(max(warmup, 3)):
-        gather(wl.step())
-    torch.cuda.synchronize()
+    for w, st in zip(wls, streams):
+        with torch.cuda.stream(st):
+            for _ in range(max(warmup, 3) if w is wl else 2):
+                gather(w, w.step())
+        torch.cuda.synchronize()
     outs = wl.step()
     torch.cuda.synchronize()
     ok = bool((wl.status == 0).all())
     iters_sum = float(wl.iters.sum().item())
-    evk = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    fev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    launches0 = wl.solver.kernel_count()
+
+    def timed(n_steps, lanes):
+        """n_steps solves round-robin over the first `lanes` handles / streams; returns (region ms, sum of the
+        per-launch durations, flush ms that can be subtracted)"""
+        evk = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
+        fev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_start.record(main)
+        for st in streams[:lanes]:
+            if st is not main:
+                st.wait_event(t_start)
+        o = None
+        for k in range(n_steps):
+            w, st = wls[k % lanes], streams[k % lanes]
+            with torch.cuda.stream(st):
+                fev[k][0].record()
+                if not os.environ.get("BENCH_NO_FLUSH"):
+                    flush[k % lanes].fill_(float(k))            # evict L2
+                fev[k][1].record()
+                evk[k][0].record()
+                o = w.step()
+                evk[k][1].record()
+                gather(w, o)
+        for st in streams[:lanes]:
+            if st is not main:
+                main.wait_stream(st)
+        t_end.record(main)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        # one batch at a time: the flush is a separate interval of the region and is taken out; overlapped: it
+        # runs underneath the other batch and stays in
+        flush_ms = sum(a.elapsed_time(b) for a, b in fev) if lanes == 1 else 0.0
+        return t_start.elapsed_time(t_end) - flush_ms, sum(a.elapsed_time(b) for a, b in evk), o
+
+    launches0 = sum(w.solver.kernel_count() for w in wls)
     if sampler is not None:
         sampler.start()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_start.record()
-    for k in range(steps):
-        fev[k][0].record()
-        flush.fill_(float(k))                       # evict L2; its duration is subtracted below
-        fev[k][1].record()
-        evk[k][0].record()
-        outs = wl.step()
-        evk[k][1].record()
-        gather(outs)
-    t_end.record()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    t_ms, tk_ms, outs = timed(steps, F)
     if sampler is not None:
         sampler.stop()
-    launches = wl.solver.kernel_count() - launches0
-    flush_ms = sum(a.elapsed_time(b) for a, b in fev)
-    t_ms = t_start.elapsed_time(t_end) - flush_ms
-    tk_ms = sum(a.elapsed_time(b) for a, b in evk)
-    print("rank %d [%s]: %.3f ms per step in the timed region, %.3f ms per solve launch" %
-          (rank, wl.key, t_ms / steps, tk_ms / steps), file=sys.stderr)
-    tt = torch.tensor([t_ms, tk_ms], dtype=torch.float64, device=dev)
+    launches = sum(w.solver.kernel_count() for w in wls) - launches0
+    if F > 1:
+        tk_ms = t_ms                    # overlapped launches: the average launch duration is the region / K
+        s_steps = max(3, min(steps, 5))
+        s_ms, sk_ms, _ = timed(s_steps, 1)
+        serial = {"ms_per_step": s_ms / s_steps, "kernel_ms": sk_ms / s_steps, "steps": s_steps}
+    else:
+        serial = None
+    print("rank %d [%s]: %.3f ms per step in the timed region (%d in flight), %.3f ms per solve launch%s" %
+          (rank, wl.key, t_ms / steps, F, tk_ms / steps,
+           "" if serial is None else "; one batch at a time: %.3f ms per step" % serial["ms_per_step"]), file=sys.stderr)
+    tt = torch.tensor([t_ms, tk_ms] + ([serial["ms_per_step"], serial["kernel_ms"]] if serial else []),
+                      dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_ms, tk_ms = float(tt[0]), float(tt[1])
     n_solves = wl.solves_per_step()
     value = world * n_solves * steps / (t_ms * 1e-3)
+    if serial:
+        serial["ms_per_step"], serial["kernel_ms"] = float(tt[2]), float(tt[3])
+        serial["value"] = world * n_solves / (serial["ms_per_step"] * 1e-3)
 
-    # ---- end to end: host buffers in, host results out, the NCCL gather of the results included ----
-    wl.host_step()
-    e2e_steps = max(3, min(steps, 5))
+    # ---- end to end: host buffers in, host results out, the NCCL gather of the results included.  F callers (one
+    # host thread per handle, as F workers of a service would) keep F batches in flight: the copies of one batch run
+    # underneath the solve of the other.  Results are consumed (and gathered) in step order. ----
+    for w in wls:
+        w.host_step()
+    e2e_steps = max(3, min(steps, 5)) * F
+    pools = [ThreadPoolExecutor(1) for _ in wls]
+
+    def host_job(w, st):
+        with torch.cuda.device(dev), torch.cuda.stream(st):
+            res = w.host_step()
+            if world > 1 and gather_mode != "none":
+                res = [r.to(dev, non_blocking=True) for r in res]      # (the page-locked result arrays are reused)
+                st.synchronize()
+            return res
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        res = wl.host_step()
+    futs = [pools[k % F].submit(host_job, wls[k % F], streams[k % F]) for k in range(e2e_steps)]
+    for k, fu in enumerate(futs):
+        res = fu.result()
         if world > 1 and gather_mode != "none":
-            gather([r.to(dev, non_blocking=True) for r in res])
+            gather(wls[k % F], res)
             torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    for pl in pools:
+        pl.shutdown()
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -568,9 +630,10 @@ def measure(wl, args, world, rank, dev, gather_mode, steps, warmup, sampler=None
     h2d, d2h = wl.io_bytes()
 
     out = {"value": value, "ms_per_step": t_ms / steps, "kernel_ms": tk_ms / steps, "launches": int(launches),
-           "iters_sum": iters_sum, "n_solves": n_solves, "ok": ok,
+           "iters_sum": iters_sum, "n_solves": n_solves, "ok": ok, "inflight": F, "serial": serial,
            "e2e": {"value": e2e_value, "unit": "solves/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                   "steps": e2e_steps, "includes_gather": bool(world > 1 and gather_mode != "none")},
+                   "steps": e2e_steps, "batches_in_flight": F,
+                   "includes_gather": bool(world > 1 and gather_mode != "none")},
            "outs": outs}
     if with_latency and not wl.closed_loop:
         lat = wl.solver.enable_latency(wl.B)
@@ -579,6 +642,7 @@ def measure(wl, args, world, rank, dev, gather_mode, steps, warmup, sampler=None
         lat_us = lat.cpu().numpy() / 1e3
         wl.solver.disable_latency()
         out["p50_solve_us"], out["p99_solve_us"] = float(np.median(lat_us)), float(np.percentile(lat_us, 99))
+    del wls[1:]
     return out
 
 
@@ -616,6 +680,10 @@ def main():
     ap.add_argument("--layout", type=int, default=S.LAYOUT_AUTO)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="do not attach short runs of the other configurations")
+    ap.add_argument("--inflight", type=int, default=1,
+                    help="batches in flight: the K steps alternate over this many solver handles / streams.  Measured "
+                         "(one B200): C2 15.2 -> 14.5..14.9 ms, C4 98.8 -> 59.4 ms, C4 Frenet 50.8 -> 41.1 ms per step with 2; no "
+                         "gain at N > 1, where the NCCL gathers order the streams - so the default stays 1")
     ap.add_argument("--gather", default="inline", choices=["inline", "none"],
                     help="N>1: NCCL gather of the results in stream order after each step (none: diagnostic)")
     args = ap.parse_args()
@@ -639,7 +707,9 @@ def main():
     wl = CONFIGS[args.config](batch=args.batch, rank=rank)
     wl.setup(mv, dev, args.layout)
     sampler = ClockSampler(local) if rank == 0 and not os.environ.get("BENCH_NO_SAMPLER") else None
-    m = measure(wl, args, world, rank, dev, args.gather, args.steps, args.warmup, sampler, with_latency=True)
+    inflight = 1 if wl.key == "c1" else max(1, args.inflight)
+    m = measure(wl, args, world, rank, dev, args.gather, args.steps, args.warmup, sampler, with_latency=True,
+                inflight=inflight)
     assert m["ok"], "solver failures in the benchmark batch"
 
     peaks = {}
@@ -659,8 +729,10 @@ def main():
             try:
                 w2 = CONFIGS[key](rank=rank)
                 w2.setup(mv, dev, S.LAYOUT_AUTO)
-                m2 = measure(w2, args, world, rank, dev, args.gather, 2, 3)
-                o = {"config": config_block(w2, world), "value": m2["value"], "unit": "solves/s", "ms_per_step": m2["ms_per_step"],
+                f2 = 1 if key == "c1" else max(1, args.inflight)
+                m2 = measure(w2, args, world, rank, dev, args.gather, 2 * f2, 3, inflight=f2)
+                o = {"config": config_block(w2, world, {"batches_in_flight": f2}), "value": m2["value"], "unit": "solves/s",
+                     "ms_per_step": m2["ms_per_step"], "serial": m2["serial"],
                      "all_succeeded": m2["ok"], "mean_ipm_iters": m2["iters_sum"] / m2["n_solves"], "e2e": m2["e2e"],
                      "gpu_launches": m2["launches"], "roofline": roofline_of(w2, m2, peak_tf, hbm_peak, hbm_src)}
                 if rank == 0:
@@ -724,10 +796,12 @@ def main():
         "warmup": max(args.warmup, 3), "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_block(wl, world, {
-            "l2": "flushed between steps (256 MB write)",
+            "l2": "flushed between steps (256 MB write)", "batches_in_flight": inflight,
             "layout": {0: "auto", 1: "thread-per-problem", 2: "warp-per-problem", 3: "phase kernels", 4: "CTA-resident"}[args.layout],
             "parallelism": "problem-index sharding x%d, NCCL all-gather of results + stats (%s)" % (world, args.gather)}),
         "e2e": m["e2e"],
+        "serial": m["serial"],
+        "serial_note": "the same batch with ONE batch in flight (one handle, one stream: the round-1 arrangement)",
         "gpu_launches": m["launches"],
         "clocks": sampler.summary() if sampler is not None else None,
         "roofline": roofline_of(wl, m, peak_tf, hbm_peak, hbm_src),
