@@ -302,6 +302,14 @@ int64_t mpcv_launch_count(const mpcv_handle* h);
    graph-driven sweep (which mpcv_launch_count cannot see from the host).  Either out may be NULL. */
 int mpcv_phase_sweeps(mpcv_handle* h, int32_t* sweeps, int64_t* kernel_nodes, void* stream);
 
+/* Diagnostic counters accumulated by the kernels since the handle was created (synchronises the device):
+   counters4[0] = filter overflows.  IPOPT's line-search filter (the reference's solver, IpFilter.cpp) is unbounded;
+   the device filter holds 16 entries after IPOPT's own pruning of dominated entries and drops the oldest when full.
+   A non-zero count says some solve of this handle left IPOPT's iteration path for that reason (never on the
+   BASELINE configurations; about 1 in 2,000 of the all-zeros-guess problems of SURVEY Appendix E).
+   counters4[1..3] are reserved (0). */
+int mpcv_diag(mpcv_handle* h, uint64_t* counters4);
+
 #ifdef __cplusplus
 }
 #endif

@@ -170,6 +170,11 @@ mpcv_handle* mpcv_create(const mpcv_spec* s) {
       cudaEventCreateWithFlags(&h->last_done, cudaEventDisableTiming) != cudaSuccess) {
     mpcv_set_error(-EIO, "cudaStreamCreate"); delete h; return nullptr;
   }
+  // diagnostic counters the kernels bump (Params::diag): [0] filter overflows
+  if (cudaMalloc(&h->P.diag, 4 * sizeof(unsigned long long)) != cudaSuccess ||
+      cudaMemset(h->P.diag, 0, 4 * sizeof(unsigned long long)) != cudaSuccess) {
+    mpcv_set_error(-EIO, "cudaMalloc (diagnostic counters)"); mpcv_destroy(h); return nullptr;
+  }
   return h;
 }
 
@@ -181,7 +186,16 @@ void mpcv_destroy(mpcv_handle* h) {
   if (h->dstage) cudaFree(h->dstage);
   if (h->own_stream) cudaStreamDestroy(h->own_stream);
   if (h->last_done) cudaEventDestroy(h->last_done);
+  if (h->P.diag) cudaFree(h->P.diag);
   delete h;
+}
+
+int mpcv_diag(mpcv_handle* h, uint64_t* counters4) {
+  if (!h || !counters4) return mpcv_set_error(-EINVAL, "mpcv_diag: null argument");
+  if (cudaDeviceSynchronize() != cudaSuccess ||
+      cudaMemcpy(counters4, h->P.diag, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return mpcv_set_error(-EIO, "mpcv_diag: copy failed");
+  return 0;
 }
 
 int64_t mpcv_launch_count(const mpcv_handle* h) { return h ? h->launches : 0; }

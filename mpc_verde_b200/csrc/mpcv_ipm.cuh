@@ -121,7 +121,7 @@ struct Layout {
 
 // Relaxed bounds of one variable, precomputed once per kernel (the bounds are shared by the batch).
 struct BndEntry { double lo, hi; int flags, pad; };   // flags: 1 = lower, 2 = upper, 4 = fixed
-constexpr int kStateSlots = 40;
+constexpr int kStateSlots = 56;    // 0..15 scalars, 16..31 filter phi, 32..39 scalars, 40..55 filter theta
 constexpr int kSlotDwHint = 34;   // phase pipeline: delta_w found by the parallel probe (> 0) or -(last delta_w probed)
 constexpr int kRunning = 1000;    // internal "not finished" status
 
@@ -186,7 +186,7 @@ struct Ipm {
   static constexpr int NX = Model::NX, NU = Model::NU, NZ = NX + NU;
   static constexpr int NW = NZ * (NZ + 1) / 2, NPX = NX * (NX + 1) / 2, NF = NU * (NU + 1) / 2;
   static constexpr int NAB = NX * NX + NX * NU, NRIC = NU * NX + NU + NF, NPP = NPX + NX;
-  static constexpr int FILTER_MAX = 8;
+  static constexpr int FILTER_MAX = 16;
 
   const Params& P;
   const Layout& L;
@@ -208,7 +208,39 @@ struct Ipm {
   int acc_count;        // consecutive iterates within the acceptable tolerances
   double f_last;        // objective at the previous convergence test
   MPCV_D double& fil_phi(int q) const { return ws[L.st + 16 + q]; }
-  MPCV_D double& fil_th(int q) const { return ws[L.st + 24 + q]; }
+  MPCV_D double& fil_th(int q) const { return ws[L.st + 40 + q]; }
+  // Filter augmentation as IPOPT's Filter::AddEntry does it: entries the new one dominates (both coordinates >= the
+  // new ones) leave the filter first — whatever they reject, the new entry rejects too.  IPOPT's filter is
+  // unbounded; this one holds FILTER_MAX entries (the largest filter over the cold-started C2 batch is 5, over the
+  // all-zeros-guess batch of SURVEY Appendix E 17: tests/test_oracle_golden.py), drops the OLDEST entry when full and
+  // counts that in the handle's diagnostics (Params::diag[0], mpcv_diag).  Every lane computes the same survivor
+  // count from the same reads; lane 0 rewrites the entries.
+  MPCV_D void filter_add(double phi_e, double th_e) {
+    int kept = 0;
+    unsigned keep = 0u;
+    for (int q = 0; q < nfil; ++q) {
+      if (!(fil_phi(q) >= phi_e && fil_th(q) >= th_e)) { keep |= 1u << q; ++kept; }
+    }
+    g.sync();                      // all lanes have read the entries
+    if (g.lane == 0) {
+      int k = 0;
+      for (int q = 0; q < nfil; ++q) {
+        if (keep & (1u << q)) { if (k != q) { fil_phi(k) = fil_phi(q); fil_th(k) = fil_th(q); } ++k; }
+      }
+      if (kept == FILTER_MAX) {    // full: the oldest entry goes
+        for (int q = 1; q < FILTER_MAX; ++q) { fil_phi(q - 1) = fil_phi(q); fil_th(q - 1) = fil_th(q); }
+#if defined(__CUDA_ARCH__)
+        if (P.diag) atomicAdd(P.diag, 1ull);
+#else
+        if (P.diag) ++*P.diag;
+#endif
+      }
+      const int at = kept == FILTER_MAX ? FILTER_MAX - 1 : kept;
+      fil_phi(at) = phi_e; fil_th(at) = th_e;
+    }
+    nfil = kept == FILTER_MAX ? FILTER_MAX : kept + 1;
+    g.sync();
+  }
   // search direction -> line search hand-over
   double ls_alpha_max, ls_theta, ls_gBD, ls_phi;
   // barrier log-sum of the current iterate = log-sum of the trial point accepted last (same slacks): reused by
@@ -1801,15 +1833,7 @@ struct Ipm {
   MPCV_D void ls_filter_augment(double alpha_test, double phi_acc, const LsPow& pw) {
     const double theta = ls_theta, phi = ls_phi;
     if (!ls_is_ftype(alpha_test, pw) || !ls_armijo(alpha_test, phi_acc)) {
-      // (one lane writes; the step that follows synchronises the group before the filter is read again)
-      if (nfil < FILTER_MAX) {
-        if (g.lane == 0) { fil_phi(nfil) = phi - 1e-8 * theta; fil_th(nfil) = (1.0 - 1e-5) * theta; }
-        ++nfil;
-      } else if (g.lane == 0) {
-        // filter full: drop the oldest entry
-        for (int q = 1; q < FILTER_MAX; ++q) { fil_phi(q - 1) = fil_phi(q); fil_th(q - 1) = fil_th(q); }
-        fil_phi(FILTER_MAX - 1) = phi - 1e-8 * theta; fil_th(FILTER_MAX - 1) = (1.0 - 1e-5) * theta;
-      }
+      filter_add(phi - 1e-8 * theta, (1.0 - 1e-5) * theta);
     }
   }
   MPCV_D void ls_take_step(double alpha) {
@@ -1927,14 +1951,7 @@ struct Ipm {
     const double theta_R = ls_theta, phi_R = ls_phi;
     if (!(theta_R > P.tol)) return MPCV_RESTORATION_FAILED;          // (almost) feasible: nothing to restore
     // the point we leave goes into the filter
-    if (nfil < FILTER_MAX) {
-      if (g.lane == 0) { fil_phi(nfil) = phi_R - 1e-8 * theta_R; fil_th(nfil) = (1.0 - 1e-5) * theta_R; }
-      ++nfil;
-    } else if (g.lane == 0) {
-      for (int q = 1; q < FILTER_MAX; ++q) { fil_phi(q - 1) = fil_phi(q); fil_th(q - 1) = fil_th(q); }
-      fil_phi(FILTER_MAX - 1) = phi_R - 1e-8 * theta_R; fil_th(FILTER_MAX - 1) = (1.0 - 1e-5) * theta_R;
-    }
-    g.sync();
+    filter_add(phi_R - 1e-8 * theta_R, (1.0 - 1e-5) * theta_R);
     double theta = theta_R;
     bool done = false;
     for (int r = 0; r < kRestoMaxIter && !done; ++r) {

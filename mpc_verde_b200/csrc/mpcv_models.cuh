@@ -46,6 +46,7 @@ struct Params {
   double dual_inf_tol, constr_viol_tol, compl_inf_tol;
   double acceptable_tol, acceptable_obj_change_tol;
   int max_iter, max_soc, acceptable_iter;
+  unsigned long long* diag;   // optional diagnostic counters (device memory in the kernels): [0] filter overflows
 };
 
 MPCV_HD void sincos_(double a, double* s, double* c) {
@@ -55,6 +56,15 @@ MPCV_HD void sincos_(double a, double* s, double* c) {
   *s = sin(a);
   *c = cos(a);
 #endif
+}
+
+// (sin, cos)(a + d) from (sin, cos)(a) and (sin, cos)(d).  The stage headings of an RK4 interval are th + j (h/2) w,
+// j = 0..2M: two sincos and 2M rotations instead of 2M + 1 sincos (FP64 sincos is a ~40-instruction software
+// sequence; it was half of the unicycle's instruction count).  Each rotation adds <= 2 ulp: <= 2e-15 after the 8 of
+// M = 4, far inside the 1e-12 RK4 budget of SURVEY 8c.
+MPCV_HD void rot_(double s, double c, double sd, double cd, double* s1, double* c1) {
+  *s1 = s * cd + c * sd;
+  *c1 = c * cd - s * sd;
 }
 
 MPCV_HD double rsqrt_(double a) {
@@ -116,16 +126,17 @@ struct Unicycle {
     const double h = P.T / M, hh = 0.5 * h, h6 = h / 6.0;
     double X = x[0], Y = x[1];
     double qa = 0.0;
-    double s0, c0;
+    double s0, c0, sd, cd;
     sincos_(th, &s0, &c0);
+    sincos_(hh * w, &sd, &cd);      // every stage heading is th + j (h/2) w: one rotation per half step (see rot_)
     double xr = 0, yr = 0, tr = 0;
     if (KIND == 0) { xr = pg[0]; yr = pg[1]; tr = pg[2]; }
     const double uc = P.R[0] * v * v + P.R[1] * w * w;
     for (int j = 0; j < M; ++j) {
       const double a0 = th + (2 * j) * hh * w, a1 = th + (2 * j + 1) * hh * w, a2 = th + (2 * j + 2) * hh * w;
       double s1, c1, s2, c2;
-      sincos_(a1, &s1, &c1);
-      sincos_(a2, &s2, &c2);
+      rot_(s0, c0, sd, cd, &s1, &c1);
+      rot_(s1, c1, sd, cd, &s2, &c2);
       if (KIND == 0) {
         // L at the four RK4 stage states (k1_q..k4_q of MS:106-112)
         double ex, ey, et, L1, L2, L3, L4;
@@ -221,16 +232,17 @@ struct Unicycle {
     } else {
       const int M = P.M;
       const double h = P.T / M, hh = 0.5 * h, h6 = h / 6.0;
-      double s0, c0;
+      double s0, c0, sd, cd;
       sincos_(th, &s0, &c0);
+      sincos_(hh * w, &sd, &cd);
       double xr = 0, yr = 0, tr = 0;
       if (KIND == 0) { xr = pg[0]; yr = pg[1]; tr = pg[2]; }
       const double ex = x[0] - xr, ey = x[1] - yr;
       for (int j = 0; j < M; ++j) {
         const double t0 = (2 * j) * hh, t1 = (2 * j + 1) * hh, t2 = (2 * j + 2) * hh;
         double s1, c1, s2, c2;
-        sincos_(th + t1 * w, &s1, &c1);
-        sincos_(th + t2 * w, &s2, &c2);
+        rot_(s0, c0, sd, cd, &s1, &c1);
+        rot_(s1, c1, sd, cd, &s2, &c2);
         if (KIND == 0) {
           Sums sp;
           // k1 point: base

@@ -30,6 +30,7 @@ inline Params params_from_spec(const mpcv_spec& s) {
   P.acceptable_tol = s.acceptable_tol > 0 ? s.acceptable_tol : 1e-6;
   P.acceptable_iter = s.acceptable_iter != 0 ? s.acceptable_iter : 15;
   P.acceptable_obj_change_tol = s.acceptable_obj_change_tol > 0 ? s.acceptable_obj_change_tol : 1e20;
+  P.diag = nullptr;
   return P;
 }
 

@@ -93,6 +93,15 @@ class NlpSolver:
     def launch_count(self):
         return int(self._handle.lib.mpcv_launch_count(self._handle.h))
 
+    def diagnostics(self):
+        """Counters the kernels keep since the solver was created: `filter_overflows` (the 16-entry device filter had
+        to drop its oldest entry; IPOPT's filter is unbounded)."""
+        import ctypes as C
+        c = (C.c_uint64 * 4)()
+        with torch.cuda.device(self.device):
+            _lib.check(self._handle.lib.mpcv_diag(self._handle.h, c), "mpcv_diag")
+        return {"filter_overflows": int(c[0])}
+
     def _phase_counts(self):
         import ctypes as C
         n, k = C.c_int32(0), C.c_int64(0)

@@ -347,6 +347,7 @@ void chol_solve(const std::vector<double>& L, int n, double* b) {
 struct SolveStats {
   int status = 0, iters = 0;
   int n_inertia_corrections = 0, n_backtracks = 0, n_soc = 0;
+  int max_filter = 0, n_resto = 0;   // largest filter of the solve; restoration steps taken
   double f = 0, mu = 0, err = 0, df = 1;
 };
 
@@ -857,6 +858,16 @@ class Ipm {
     }
 
     std::vector<std::pair<double, double>> filter;   // (phi, theta) entries
+    // IPOPT's Filter::AddEntry: entries the new one dominates (both coordinates >= the new ones) leave the filter —
+    // whatever they reject, the new entry rejects too
+    auto filter_add = [&](double phi_e, double th_e) {
+      size_t k = 0;
+      for (size_t q = 0; q < filter.size(); ++q)
+        if (!(filter[q].first >= phi_e && filter[q].second >= th_e)) filter[k++] = filter[q];
+      filter.resize(k);
+      filter.emplace_back(phi_e, th_e);
+      st.max_filter = std::max(st.max_filter, (int)filter.size());
+    };
     double theta_max = -1, theta_min = -1;
     double delta_w_last = 0.0;
     std::vector<double> sigma(n), r(n), d, lamplus, dzl(n), dzu(n), wt(n), ct(std::max(m, 1));
@@ -1032,7 +1043,7 @@ class Ipm {
         const bool dbg = getenv("MPCO_DEBUG_RESTO") != nullptr;
         if (dbg) fprintf(stderr, "resto enter iter %d theta %.3e phi %.6e alpha_min %.3e gBD %.3e nfil %zu\n", iter, theta, phi, alpha_min, gBD, filter.size());
         if (!single && theta > opt.tol) {
-          filter.emplace_back(phi - opt.gamma_phi * theta, (1.0 - opt.gamma_theta) * theta);
+          filter_add(phi - opt.gamma_phi * theta, (1.0 - opt.gamma_theta) * theta);
           const double theta_R = theta;
           double th = theta_R;
           std::vector<double> sigR(n, 0.0), r0(n, 0.0), dr, lr, cc;
@@ -1059,6 +1070,7 @@ class Ipm {
             if (!found) break;
             for (int i = 0; i < n; ++i) w[i] = wt[i];
             ++n_resto;
+            ++st.n_resto;
             th = theta_t;
             eval_derivatives();
             bool fok = std::isfinite(phi_t) && !(theta_max > 0 && theta_t > theta_max);
@@ -1085,7 +1097,7 @@ class Ipm {
         phi_t = 0; theta_t = 0; (void)phi_t; (void)theta_t;
         double phi_acc = barrier(wt, eval_f_c(wt, ct));
         if (!is_ftype(alpha_test) || !armijo(alpha_test, phi_acc))
-          filter.emplace_back(phi - opt.gamma_phi * theta, (1.0 - opt.gamma_theta) * theta);
+          filter_add(phi - opt.gamma_phi * theta, (1.0 - opt.gamma_theta) * theta);
       }
       double alpha_dual = ftb_dual();
       // accept: primal + equality multipliers with alpha (alpha_for_y=primal), bound multipliers with alpha_dual
@@ -1166,7 +1178,7 @@ void solve_range(const mpcv_spec& s, const double* x0, const double* lbx, const 
     if (stats) {
       double* o = stats + b * 8;
       o[0] = ipm.st.n_inertia_corrections; o[1] = ipm.st.n_backtracks; o[2] = ipm.st.n_soc;
-      o[3] = ipm.st.mu; o[4] = ipm.st.err; o[5] = ipm.st.df; o[6] = 0; o[7] = 0;
+      o[3] = ipm.st.mu; o[4] = ipm.st.err; o[5] = ipm.st.df; o[6] = ipm.st.max_filter; o[7] = ipm.st.n_resto;
     }
   }
 }

@@ -14,9 +14,12 @@
 
 using namespace mpcv;
 
+static unsigned long long g_diag[4] = {0, 0, 0, 0};
+
 template <class Model, bool SINGLE>
 static int hs_solve_t(const mpcv_spec* s, const SolveIO& io, long B) {
   Params P = params_from_spec(*s);
+  P.diag = g_diag;
   Layout L = make_layout<Model, SINGLE>(s->N);
   std::vector<double> buf(L.total);
   for (long b = 0; b < B; ++b) {
@@ -32,6 +35,7 @@ template <class Model>
 static int hs_solve_phased_t(const mpcv_spec* s, const SolveIO& io, long B, int* sweeps_out) {
   using Ph = Phase<Model, WsDense>;
   Params P = params_from_spec(*s);
+  P.diag = g_diag;
   Layout L = make_layout<Model, false>(s->N);
   std::vector<double> slab((size_t)L.total * B, 0.0);
   auto ws = [&](long b) { return WsDense{slab.data() + (size_t)b * L.total}; };
@@ -106,6 +110,7 @@ static int hs_solve_phased_t(const mpcv_spec* s, const SolveIO& io, long B, int*
 template <class Model, bool SINGLE>
 static int hs_loop_t(const mpcv_spec* s, const LoopIO& io, long B) {
   Params P = params_from_spec(*s);
+  P.diag = g_diag;
   Layout L = make_layout<Model, SINGLE>(s->N);
   std::vector<double> buf(L.total);
   for (long b = 0; b < B; ++b) {
@@ -120,6 +125,7 @@ static int hs_der_t(const mpcv_spec* s, const double* z, const double* pstage, c
                     double* A, double* Bm, double* q, double* grad, double* H, long B) {
   constexpr int NX = Model::NX, NU = Model::NU, NZ = NX + NU, NW = NZ * (NZ + 1) / 2;
   Params P = params_from_spec(*s);
+  P.diag = g_diag;
   for (long b = 0; b < B; ++b) {
     const double* pp = pstage + b * (Model::NPG + Model::NPS);
     double W[NW], xv[NX], qv;
@@ -151,6 +157,9 @@ static int hs_der_t(const mpcv_spec* s, const double* z, const double* pstage, c
 #define HS_COMMA ,
 
 extern "C" {
+
+// diagnostic counters of the device headers (Params::diag): [0] filter overflows since the library was loaded
+unsigned long long hs_filter_overflows() { return g_diag[0]; }
 
 int hs_solve(const mpcv_spec* s, const double* x0, const double* lbx, const double* ubx, const double* p,
              double* x, double* f, double* g, double* lam_g, double* lam_x, int* status, int* iters, long B) {

@@ -65,6 +65,13 @@ def solve(spec, x0, lbx, ubx, p, phased=False, libpath=None):
     return out
 
 
+def filter_overflows():
+    """times the 16-entry filter of the device headers dropped its oldest entry since the harness was loaded"""
+    f = lib().hs_filter_overflows
+    f.restype = C.c_ulonglong
+    return int(f())
+
+
 def stage_derivs(spec, z, pstage, lam):
     z = _f64(z); lam = _f64(lam)
     B = z.shape[0]

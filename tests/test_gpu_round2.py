@@ -355,6 +355,20 @@ def test_zeros_guess_batch_recovers_through_restoration(mv, layout):
     assert same.mean() >= 0.97, same.mean()
     assert np.abs(sol["x"].cpu().numpy()[same] - ref["x"][same]).max() <= 1e-8
     assert np.abs(sol["f"].cpu().numpy()[same] - ref["f"][same]).max() <= 1e-8 * np.abs(ref["f"]).max()
+    # the filters of this batch grow past the 8 entries the round-1 filter held (oracle: up to 17); the 16-entry
+    # device filter with IPOPT's pruning of dominated entries follows them and reports when it had to drop one
+    assert solver.diagnostics()["filter_overflows"] <= 2
+
+
+def test_diagnostics_are_clean_on_the_baseline_batch(mv):
+    import torch
+    prob = problems.unicycle_multiple_shooting()
+    sp = prob["spec"]
+    x0s, p = common.unicycle_batch(4096)
+    lbx, ubx = problems.unicycle_bounds(sp, x_box=20.0)
+    solver = _solver(mv, prob)
+    solver(x0=torch.as_tensor(problems.cold_start(sp, x0s)).cuda(), lbx=lbx, ubx=ubx, p=torch.as_tensor(p).cuda())
+    assert solver.stats()["success"] and solver.diagnostics() == {"filter_overflows": 0}
 
 
 def test_one_sided_bounds_are_damped_like_the_oracle(mv):

@@ -189,3 +189,26 @@ def test_restoration_and_one_sided_damping_oracle_vs_device_headers():
     a, b = O.solve(sp, w0, lbx, ubx, p), H.solve(sp, w0, lbx, ubx, p)
     assert np.all(a["status"] == 0) and np.array_equal(a["iters"], b["iters"])
     assert np.abs(a["x"] - b["x"]).max() <= 1e-9
+
+
+def test_filter_follows_ipopt_beyond_eight_entries():
+    """the device filter used to hold 8 entries and evict the oldest, IPOPT's is unbounded.  Now both the
+    oracle and the device headers prune dominated entries the way IPOPT's Filter::AddEntry does; the oracle stays
+    unbounded, the device filter holds 16 and counts overflows.  On the hard all-zeros-guess batch the oracle's
+    filters grow past 8 (that is what the old cap truncated) and the two implementations still walk the same path."""
+    sp = S.unicycle_multiple_shooting()
+    x0s, p = common.unicycle_batch(768, seed=77)
+    lbx, ubx = problems.unicycle_bounds(sp)
+    a = O.solve(sp, None, lbx, ubx, p, want_stats=True)
+    before = H.filter_overflows()
+    b = H.solve(sp, None, lbx, ubx, p)
+    big = a["stats"][:, 6] > 8
+    assert big.sum() >= 5                                      # the sample does exercise filters beyond the old cap
+    assert np.array_equal(a["status"], b["status"])
+    assert np.array_equal(a["iters"][big], b["iters"][big])
+    assert H.filter_overflows() - before <= int((a["stats"][:, 6] > 16).sum()) + 1
+    # the BASELINE workload never comes near the cap
+    x0s, p = common.unicycle_batch(1024)
+    lbx, ubx = problems.unicycle_bounds(sp, x_box=20.0)
+    c = O.solve(sp, problems.cold_start(sp, x0s), lbx, ubx, p, want_stats=True)
+    assert c["stats"][:, 6].max() <= 8
