@@ -116,6 +116,8 @@ struct Layout {
   int sig, rb;   // Sigma_i and barrier-gradient r_i of the current iterate (filled once per iteration)
   int qs;        // per-stage interval costs (stage-parallel kernels hand them to the per-problem reduction)
   int st;        // persistent scalar state of the solve (phase-kernel pipeline), kStateSlots doubles
+  int park;      // where the second-order correction parks the plain step (n + m doubles): the Hessian blocks, or a region
+                 // of its own when the model keeps ONE copy of them for all stages (Model::LTI)
   int total;
 };
 
@@ -139,7 +141,11 @@ MPCV_HD Layout make_layout(int N) {
   // hw, ric, pp (Riccati kernels only) come last; ph_repack_kernel relies on ric, pp being the last two.
   int o = 0;
   L.lamp = L.c = L.ct = L.ric = L.pp = L.xs = L.hred = L.gam = L.tmp = 0;
-  L.ab = o; o += N * (NX * NX + NX * NU);
+  // Linear time-invariant models with a constant cost Hessian (Model::LTI): A_k, B_k, W_k are the same for every
+  // stage of a solve — ONE copy (a second for the stages folded by move blocking) instead of N; every reader finds it
+  // in L1.  C3 (N = 40): 2,040 of 5,700 doubles per problem, and the most-read ones, leave the slab.
+  const int ncopy = (Model::LTI && !SINGLE) ? 2 : N;
+  L.ab = o; o += ncopy * (NX * NX + NX * NU);
   L.grad = o; o += L.n;
   L.sig = o; o += L.n;
   L.rb = o; o += L.n;
@@ -156,7 +162,9 @@ MPCV_HD Layout make_layout(int N) {
     L.ct = o; o += L.m;
   }
   L.par = o; o += NX + Model::NPG + N * Model::NPS + 2;   // +2: alignment slack for bulk-staged stage params
-  L.hw = o; o += N * (NZ * (NZ + 1) / 2);
+  L.hw = o; o += ncopy * (NZ * (NZ + 1) / 2);
+  L.park = L.hw;
+  if (Model::LTI && !SINGLE) { L.park = o; o += L.n + L.m; }
   if (SINGLE) {
     L.xs = o; o += NX * (N + 1);
     L.hred = o; o += (NU * N) * (NU * N + 1) / 2;
@@ -281,6 +289,9 @@ struct Ipm {
   MPCV_D int ix(int k, int i) const { return k * NZ + i; }            // multiple shooting only
   MPCV_D int iu(int k, int i) const { return SINGLE ? k * NU + i : k * NZ + NX + i; }
   MPCV_D bool blocked(int k) const { return Model::HAS_UPREV && P.ntu > 0 && k >= P.ntu; }
+  // storage index of stage k's (A, B) and Hessian blocks: the stage itself, or one of the two shared copies
+  static constexpr bool kSharedStages = Model::LTI && !SINGLE;
+  MPCV_D int sk(int k) const { return kSharedStages ? (blocked(k) ? 1 : 0) : k; }
   // stage and component of variable i (multiple shooting)
   MPCV_D bool var_is_blocked_u(int i) const {
     if (!(Model::HAS_UPREV && P.ntu > 0)) return false;
@@ -380,12 +391,12 @@ struct Ipm {
     Model::der(P, x, u, pg(), ps(k), lamn, df, want_hess, xn, A, B, &q, gq, W);
     if (blocked(k)) fold_blocked(A, B, gq, want_hess ? W : nullptr);
 #pragma unroll
-    for (int i = 0; i < NX * NX; ++i) ws[L.ab + k * NAB + i] = A[i];
+    for (int i = 0; i < NX * NX; ++i) ws[L.ab + sk(k) * NAB + i] = A[i];
 #pragma unroll
-    for (int i = 0; i < NX * NU; ++i) ws[L.ab + k * NAB + NX * NX + i] = B[i];
+    for (int i = 0; i < NX * NU; ++i) ws[L.ab + sk(k) * NAB + NX * NX + i] = B[i];
     if (want_hess) {
 #pragma unroll
-      for (int i = 0; i < NW; ++i) ws[L.hw + k * NW + i] = W[i];
+      for (int i = 0; i < NW; ++i) ws[L.hw + sk(k) * NW + i] = W[i];
     }
 #pragma unroll
     for (int i = 0; i < NX; ++i) ws[L.grad + ix(k, i)] = df * gq[i];
@@ -460,12 +471,12 @@ struct Ipm {
         if (blocked(k)) fold_blocked(A, B, gq, nullptr);
         fsum += q;
 #pragma unroll
-        for (int i = 0; i < NX * NX; ++i) ws[L.ab + k * NAB + i] = A[i];
+        for (int i = 0; i < NX * NX; ++i) ws[L.ab + sk(k) * NAB + i] = A[i];
 #pragma unroll
-        for (int i = 0; i < NX * NU; ++i) ws[L.ab + k * NAB + NX * NX + i] = B[i];
+        for (int i = 0; i < NX * NU; ++i) ws[L.ab + sk(k) * NAB + NX * NX + i] = B[i];
         // stash dq/dz in the Hessian slot until the costates are known
 #pragma unroll
-        for (int i = 0; i < NZ; ++i) ws[L.hw + k * NW + i] = gq[i];
+        for (int i = 0; i < NZ; ++i) ws[L.hw + sk(k) * NW + i] = gq[i];
 #pragma unroll
         for (int i = 0; i < NX; ++i) { x[i] = xn[i]; ws[L.xs + (k + 1) * NX + i] = xn[i]; }
       }
@@ -478,16 +489,16 @@ struct Ipm {
         double mk[NX];
 #pragma unroll
         for (int i = 0; i < NU; ++i) {
-          double v = df * ws[L.hw + k * NW + NX + i];
+          double v = df * ws[L.hw + sk(k) * NW + NX + i];
 #pragma unroll
-          for (int j = 0; j < NX; ++j) v += ws[L.ab + k * NAB + NX * NX + j * NU + i] * lamn[j];
+          for (int j = 0; j < NX; ++j) v += ws[L.ab + sk(k) * NAB + NX * NX + j * NU + i] * lamn[j];
           ws[L.grad + iu(k, i)] = v;
         }
 #pragma unroll
         for (int i = 0; i < NX; ++i) {
-          double v = df * ws[L.hw + k * NW + i];
+          double v = df * ws[L.hw + sk(k) * NW + i];
 #pragma unroll
-          for (int j = 0; j < NX; ++j) v += ws[L.ab + k * NAB + j * NX + i] * lamn[j];
+          for (int j = 0; j < NX; ++j) v += ws[L.ab + sk(k) * NAB + j * NX + i] * lamn[j];
           mk[i] = v;
         }
 #pragma unroll
@@ -503,7 +514,7 @@ struct Ipm {
           Model::der(P, x, u, pg(), ps(k), lamn, df, true, xn, A, B, &q, gq, W);
           if (blocked(k)) fold_blocked(A, B, gq, W);
 #pragma unroll
-          for (int i = 0; i < NW; ++i) ws[L.hw + k * NW + i] = W[i];
+          for (int i = 0; i < NW; ++i) ws[L.hw + sk(k) * NW + i] = W[i];
         }
       }
     }
@@ -663,7 +674,7 @@ struct Ipm {
           double d = ws[L.grad + v] - lk[i] - ws[L.zl + v] + ws[L.zu + v];
           if (k < N) {
 #pragma unroll
-            for (int j = 0; j < NX; ++j) d += ws[L.ab + k * NAB + j * NX + i] * ln[j];
+            for (int j = 0; j < NX; ++j) d += ws[L.ab + sk(k) * NAB + j * NX + i] * ln[j];
           }
           dual = fmax(dual, fabs(d));
         }
@@ -674,7 +685,7 @@ struct Ipm {
             if (bnd(v).fixed) continue;
             double d = ws[L.grad + v] - ws[L.zl + v] + ws[L.zu + v];
 #pragma unroll
-            for (int j = 0; j < NX; ++j) d += ws[L.ab + k * NAB + NX * NX + j * NU + i] * ln[j];
+            for (int j = 0; j < NX; ++j) d += ws[L.ab + sk(k) * NAB + NX * NX + j * NU + i] * ln[j];
             dual = fmax(dual, fabs(d));
           }
         }
@@ -758,19 +769,19 @@ struct Ipm {
   MPCV_D void prefetch_fac(int k, bool identity) const {
     if (LANES != 1) return;          // shared-memory workspaces have nothing to prefetch
 #pragma unroll
-    for (int i = 0; i < NAB; ++i) pf(L.ab + k * NAB + i);
+    for (int i = 0; i < NAB; ++i) pf(L.ab + sk(k) * NAB + i);
     if (!identity) {
 #pragma unroll
-      for (int i = 0; i < NW; ++i) pf(L.hw + k * NW + i);
+      for (int i = 0; i < NW; ++i) pf(L.hw + sk(k) * NW + i);
 #pragma unroll
       for (int i = 0; i < NZ; ++i) pf(L.sig + k * NZ + i);
     }
   }
   MPCV_D void load_fac(int k, bool identity, FacIn& s) const {
 #pragma unroll
-    for (int i = 0; i < NX * NX; ++i) s.A[i] = ws[L.ab + k * NAB + i];
+    for (int i = 0; i < NX * NX; ++i) s.A[i] = ws[L.ab + sk(k) * NAB + i];
 #pragma unroll
-    for (int i = 0; i < NX * NU; ++i) s.B[i] = ws[L.ab + k * NAB + NX * NX + i];
+    for (int i = 0; i < NX * NU; ++i) s.B[i] = ws[L.ab + sk(k) * NAB + NX * NX + i];
     if (identity) {
 #pragma unroll
       for (int i = 0; i < NW; ++i) s.W[i] = 0.0;
@@ -778,7 +789,7 @@ struct Ipm {
       for (int i = 0; i < NZ; ++i) { s.W[tri(i, i)] = 1.0; s.sg[i] = resto_sigma ? ws[L.sig + k * NZ + i] : 0.0; }
     } else {
 #pragma unroll
-      for (int i = 0; i < NW; ++i) s.W[i] = ws[L.hw + k * NW + i];
+      for (int i = 0; i < NW; ++i) s.W[i] = ws[L.hw + sk(k) * NW + i];
 #pragma unroll
       for (int i = 0; i < NZ; ++i) s.sg[i] = ws[L.sig + k * NZ + i];
     }
@@ -834,7 +845,7 @@ struct Ipm {
     g.sync();
     int ok = 1;
     for (int k = N - 1; k >= 0; --k) {
-      const WS ab = ws.view(L.ab + k * NAB), hw = ws.view(L.hw + k * NW), sgv = ws.view(L.sig + k * NZ);
+      const WS ab = ws.view(L.ab + sk(k) * NAB), hw = ws.view(L.hw + sk(k) * NW), sgv = ws.view(L.sig + k * NZ);
       const WS ric = ws.view(L.ric + k * NRIC), ppn = ws.view(L.pp + (k + 1) * NPP), ppk = ws.view(L.pp + k * NPP);
       // ---- step A: item c < NX = column c of (P A, G, K); item NX = the vector part (P c + p, g, kff).  One
       // instruction stream for both kinds (operands selected, not branched on): the lanes of a group stay together.
@@ -900,7 +911,7 @@ struct Ipm {
           }
         }
         // y = P a + y0:  column c: a = A[:, c], y0 = 0  (P A);  vector item: a = c_{k+1}, y0 = p_{k+1}  (P c + p)
-        const WS av = col ? ws.view(L.ab + k * NAB + it) : ws.view(coff >= 0 ? coff + (k + 1) * NX : L.ab + k * NAB);
+        const WS av = col ? ws.view(L.ab + sk(k) * NAB + it) : ws.view(coff >= 0 ? coff + (k + 1) * NX : L.ab + sk(k) * NAB);
         const int astr = col ? NX : 1;
         const bool azero = !col && coff < 0;
         double a[NX];
@@ -1223,7 +1234,7 @@ struct Ipm {
     return ws[L.rb + v];
   }
   MPCV_D void load_bwd(int k, int rmode, int coff, BwdIn& s) const {
-    const int ao = L.ab + k * NAB, ro = L.ric + k * NRIC;
+    const int ao = L.ab + sk(k) * NAB, ro = L.ric + k * NRIC;
 #pragma unroll
     for (int i = 0; i < NPX; ++i) s.P[i] = ws[L.pp + (k + 1) * NPP + i];
 #pragma unroll
@@ -1250,7 +1261,7 @@ struct Ipm {
       for (int i = 0; i < NX; ++i) pf(coff + (k + 1) * NX + i);
     }
 #pragma unroll
-    for (int i = 0; i < NAB; ++i) pf(L.ab + k * NAB + i);
+    for (int i = 0; i < NAB; ++i) pf(L.ab + sk(k) * NAB + i);
 #pragma unroll
     for (int i = 0; i < NU * NX; ++i) pf(L.ric + k * NRIC + i);
 #pragma unroll
@@ -1268,7 +1279,7 @@ struct Ipm {
 #pragma unroll
     for (int i = 0; i < NU * NX + NU; ++i) pf(L.ric + k * NRIC + i);
 #pragma unroll
-    for (int i = 0; i < NAB; ++i) pf(L.ab + k * NAB + i);
+    for (int i = 0; i < NAB; ++i) pf(L.ab + sk(k) * NAB + i);
     if (coff >= 0) {
 #pragma unroll
       for (int i = 0; i < NX; ++i) pf(coff + (k + 1) * NX + i);
@@ -1280,7 +1291,7 @@ struct Ipm {
 #pragma unroll
     for (int i = 0; i < NX; ++i) s.p[i] = ws[L.pp + k * NPP + NPX + i];
     if (k == N) return;
-    const int ao = L.ab + k * NAB, ro = L.ric + k * NRIC;
+    const int ao = L.ab + sk(k) * NAB, ro = L.ric + k * NRIC;
 #pragma unroll
     for (int i = 0; i < NU * NX; ++i) s.K[i] = ws[ro + i];
 #pragma unroll
@@ -1426,7 +1437,7 @@ struct Ipm {
 #pragma unroll
       for (int i = 0; i < NX; ++i) { dx[i] = (coff >= 0) ? ws[coff + i] : 0.0; ws[L.d + ix(0, i)] = dx[i]; }
       for (int k = 0; k < N; ++k) {
-        const WS ab = ws.view(L.ab + k * NAB), ric = ws.view(L.ric + k * NRIC);
+        const WS ab = ws.view(L.ab + sk(k) * NAB), ric = ws.view(L.ric + k * NRIC);
         double du[NU], dn[NX];
 #pragma unroll
         for (int i = 0; i < NU; ++i) {
@@ -1474,7 +1485,7 @@ struct Ipm {
         const int ncol = NU * (k + 1);
         double W[NW];
 #pragma unroll
-        for (int i = 0; i < NW; ++i) W[i] = ws[L.hw + k * NW + i];
+        for (int i = 0; i < NW; ++i) W[i] = ws[L.hw + sk(k) * NW + i];
         auto Wf = [&](int a, int b) { return a >= b ? W[tri(a, b)] : W[tri(b, a)]; };
         // T = W S  (NZ x ncol); S rows 0..NX-1 = Gamma_k, rows NX.. = unit columns of stage k
         for (int c = 0; c < ncol; ++c) {
@@ -1497,7 +1508,7 @@ struct Ipm {
           }
         }
         // Gamma_{k+1} = A Gamma_k + B E_k
-        const int ao = L.ab + k * NAB;
+        const int ao = L.ab + sk(k) * NAB;
         for (int c = 0; c < ncol; ++c) {
           double col[NX], out[NX];
 #pragma unroll
@@ -2035,13 +2046,13 @@ struct Ipm {
   // grad?  grad is live (rhs).  -> dedicated scratch: reuse `c`-sized `lamp` is live too.  We park in
   // the Hessian block storage, which is not read again until the next factorisation.
   MPCV_D void save_step() const {
-    for (int i = g.lane; i < L.n; i += LANES) ws[L.hw + i] = ws[L.d + i];
-    for (int i = g.lane; i < L.m; i += LANES) ws[L.hw + L.n + i] = ws[L.lamp + i];
+    for (int i = g.lane; i < L.n; i += LANES) ws[L.park + i] = ws[L.d + i];
+    for (int i = g.lane; i < L.m; i += LANES) ws[L.park + L.n + i] = ws[L.lamp + i];
     g.sync();
   }
   MPCV_D void restore_step() const {
-    for (int i = g.lane; i < L.n; i += LANES) ws[L.d + i] = ws[L.hw + i];
-    for (int i = g.lane; i < L.m; i += LANES) ws[L.lamp + i] = ws[L.hw + L.n + i];
+    for (int i = g.lane; i < L.n; i += LANES) ws[L.d + i] = ws[L.park + i];
+    for (int i = g.lane; i < L.m; i += LANES) ws[L.lamp + i] = ws[L.park + L.n + i];
     g.sync();
   }
   // trial evaluation for the SOC loop: c_soc <- c(x + alpha_soc d_soc) + alpha_soc * c_soc, in place in ct

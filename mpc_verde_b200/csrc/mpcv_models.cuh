@@ -101,6 +101,7 @@ struct Unicycle {
   static constexpr int NPG = (KIND == 2) ? 0 : 3;
   static constexpr int NPS = (KIND == 2) ? 5 : 0;
   static constexpr bool HAS_UPREV = false;
+  static constexpr bool LTI = false;
   static constexpr int MODEL_ID = KIND == 0 ? MPCV_MODEL_UNICYCLE_RK4_QUAD
                                 : KIND == 1 ? MPCV_MODEL_UNICYCLE_EULER_NODE
                                             : MPCV_MODEL_UNICYCLE_RK4_NODE;
@@ -322,6 +323,8 @@ struct Linear {
   static constexpr int NX = NXP + (DU ? 1 : 0), NU = 1, NZ = NX + 1;
   static constexpr int NPG = NXP * NXP + NXP, NPS = NXP + 1;
   static constexpr bool HAS_UPREV = DU;
+  // (A, B) come from the problem's parameters and the cost Hessian from the weights: the same for every stage
+  static constexpr bool LTI = true;
   static constexpr int MODEL_ID = NXP == 3 ? (DU ? MPCV_MODEL_LINEAR3_DU : MPCV_MODEL_LINEAR3)
                                            : (DU ? MPCV_MODEL_LINEAR4_DU : MPCV_MODEL_LINEAR4);
 
@@ -467,6 +470,7 @@ struct FrenetBicycle {
   static constexpr int NX = 4, NU = 2, NZ = 6;
   static constexpr int NPG = 0, NPS = 4;
   static constexpr bool HAS_UPREV = true;
+  static constexpr bool LTI = false;
   static constexpr int MODEL_ID = MPCV_MODEL_FRENET_BICYCLE;
 
   template <class PS>

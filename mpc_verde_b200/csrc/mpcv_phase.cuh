@@ -480,6 +480,7 @@ __global__ void __launch_bounds__(kPhaseThreads) ph_repack_kernel(const __grid_c
     auto live = [&](int i) {
       return i < total && !((i >= L.d && i < L.d + L.n) || (i >= L.qs && i < L.qs + L.N) ||
                             (i >= L.lamp && i < L.lamp + L.m) || (i >= L.ct && i < L.ct + L.m) ||
+                            (L.park != L.hw && i >= L.park && i < L.park + L.n + L.m) ||
                             i >= L.ric);          // ric and pp are the last two regions
     };
     const int nchunks = (total + 7) / 8;

@@ -526,26 +526,33 @@ static int launch_solve_phased(mpcv_handle* h, const SolveIO& io, long B, cudaSt
     const long share = ph_share_of(B, K);
     const int tail_cap = phase_tail_cap(h), tail_shift = phase_tail_shift(h);
     if (K > 1) CUDA_OK(cudaEventRecord(s->fork, st));
-    for (int j = 0; j < K; ++j) {
+    int rc = 0, forked = 0;
+    for (int j = 0; j < K && rc == 0; ++j) {
       const long b0 = j * share, nb = (b0 + share <= B) ? share : B - b0;
       if (nb <= 0) break;
       PhasePipe& q = s->pipe[j];
       const cudaStream_t qs = j == 0 ? st : q.stream;
-      if (j > 0) CUDA_OK(cudaStreamWaitEvent(qs, s->fork, 0));
-      if (const mpcv_host_xfer* xf = h->host_xfer)
-        for (const auto& t : xf->in)
-          if (t.host_src) CUDA_OK(cudaMemcpyAsync(t.dev + b0 * t.row_bytes, t.host_src + b0 * t.row_bytes, nb * t.row_bytes, cudaMemcpyHostToDevice, qs));
-      ph_begin_kernel<<<1, 1, 0, qs>>>(q.ctrl, q.d_io, io, B, j, K, tail_cap, tail_shift, s->res_ctrl ? &s->res_ctrl[j].next : nullptr);
-      CUDA_OK(cudaGraphLaunch(q.exec, qs));
-      if (const mpcv_host_xfer* xf = h->host_xfer)
-        for (const auto& t : xf->out)
-          if (t.host_dst) CUDA_OK(cudaMemcpyAsync(t.host_dst + b0 * t.row_bytes, t.dev + b0 * t.row_bytes, nb * t.row_bytes, cudaMemcpyDeviceToHost, qs));
-      h->launches += 6;    // begin + init chain + tail; the sweeps are counted from the device (mpcv_phase_sweeps)
-      if (j > 0) {
-        CUDA_OK(cudaEventRecord(q.done, qs));
-        CUDA_OK(cudaStreamWaitEvent(st, q.done, 0));
-      }
+      // (a failing call returns from the lambda only: the pipes forked so far are still joined below)
+      rc = [&]() -> int {
+        if (j > 0) { CUDA_OK(cudaStreamWaitEvent(qs, s->fork, 0)); forked = j; }
+        if (const mpcv_host_xfer* xf = h->host_xfer)
+          for (const auto& t : xf->in)
+            if (t.host_src) CUDA_OK(cudaMemcpyAsync(t.dev + b0 * t.row_bytes, t.host_src + b0 * t.row_bytes, nb * t.row_bytes, cudaMemcpyHostToDevice, qs));
+        ph_begin_kernel<<<1, 1, 0, qs>>>(q.ctrl, q.d_io, io, B, j, K, tail_cap, tail_shift, s->res_ctrl ? &s->res_ctrl[j].next : nullptr);
+        CUDA_OK(cudaGraphLaunch(q.exec, qs));
+        if (const mpcv_host_xfer* xf = h->host_xfer)
+          for (const auto& t : xf->out)
+            if (t.host_dst) CUDA_OK(cudaMemcpyAsync(t.host_dst + b0 * t.row_bytes, t.dev + b0 * t.row_bytes, nb * t.row_bytes, cudaMemcpyDeviceToHost, qs));
+        h->launches += 6;    // begin + init chain + tail; the sweeps are counted from the device (mpcv_phase_sweeps)
+        return 0;
+      }();
     }
+    // join: the caller's stream waits for every side stream that was forked, also after an error
+    for (int j = 1; j <= forked; ++j) {
+      PhasePipe& q = s->pipe[j];
+      if (cudaEventRecord(q.done, q.stream) == cudaSuccess) cudaStreamWaitEvent(st, q.done, 0);
+    }
+    if (rc) return rc;
     h->phase_graph_launches++;
     if (h->host_xfer) h->host_xfer_done = true;
     return 0;
