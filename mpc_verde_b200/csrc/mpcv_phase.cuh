@@ -67,7 +67,7 @@ struct PhaseCtrl {
 };
 constexpr int kRepackMin = 512;     // do not bother to repack fewer survivors than this
 #ifndef MPCV_REPACK_SPLIT
-#define MPCV_REPACK_SPLIT 4
+#define MPCV_REPACK_SPLIT 16   /* threads per survivor of the repack copy, grid = as many CTAs as the SMs hold (same box, C2 per batch: 4 threads on the thread-per-problem grid 15.3 / 15.0 ms, 4 on the full grid 14.8 / 14.7, 8: 14.4, 16: 14.35, 32: 14.65) */
 #endif
 constexpr int kRepackSplit = MPCV_REPACK_SPLIT;
 #ifndef MPCV_TAIL_BELOW

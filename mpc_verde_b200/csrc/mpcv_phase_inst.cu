@@ -203,13 +203,18 @@ static int warp_staged_mask(const mpcv_handle* h) {
 static bool warp_staged(const mpcv_handle* h) { return warp_staged_mask(h) != 0; }
 static size_t warp_smem(const mpcv_handle* h) { return warp_staged(h) ? warp_staged_smem(h) : phase_smem(h); }
 // fixed grids: enough CTAs to fill the GPU once (never more than the work of a full batch needs)
-struct PhaseGrids { unsigned prob, stage, warp, group; };
+#ifndef MPCV_REPACK_CTAS
+#define MPCV_REPACK_CTAS 11
+#endif
+struct PhaseGrids { unsigned prob, stage, warp, group, repack; };
 static PhaseGrids phase_grids(const mpcv_handle* h) {
   const long cap = h->phase->cap, sm = h->sm_count;
   const long wpb = kWarpPhaseThreads / 32;
   auto clampu = [](long need, long fill) { return (unsigned)(need < fill ? (need < 1 ? 1 : need) : fill); };
   PhaseGrids g;
   g.prob = clampu(cap / kPhaseThreads, sm * 4);
+  // the repack copy is latency-bound (kRepackSplit threads per survivor, 44 registers): as many CTAs as an SM holds
+  g.repack = clampu(cap * kRepackSplit / kPhaseThreads, sm * MPCV_REPACK_CTAS);
   g.stage = clampu(cap / kPhaseThreads * h->L.N, sm * 8);
   g.warp = clampu((cap + wpb - 1) / wpb, sm * 8);
   const long gpb = kWarpPhaseThreads / kGroupLanes;
@@ -383,7 +388,7 @@ static int phase_build_graph(mpcv_handle* h, int j) {
   void* a_tail[] = {&a, &staged_tail};
   void* a_flip[] = {&s->ctrl, &handle, &use_handle};
   if (int rc = add_kernel(body, &b_pre, nullptr, (void*)ph_pre_kernel<Model>, gr.group, kWarpPhaseThreads, smem, a_init)) return rc;
-  if (int rc = add_kernel(body, &b_repack, &b_pre, (void*)ph_repack_kernel<Model>, gr.prob, kPhaseThreads, 0, a_init)) return rc;
+  if (int rc = add_kernel(body, &b_repack, &b_pre, (void*)ph_repack_kernel<Model>, gr.repack, kPhaseThreads, 0, a_init)) return rc;
   if (int rc = add_kernel(body, &b_relist, &b_repack, (void*)ph_repack_list_kernel<Model>, gr.prob, kPhaseThreads, 0, a_init)) return rc;
   if (int rc = add_kernel(body, &b_factor, &b_relist, (void*)ph_factor_kernel<Model>, gr.prob, kPhaseThreads, smem, a_init)) return rc;
   if (int rc = add_kernel(body, &b_probe, &b_factor, (void*)ph_probe_kernel<Model>, gr.prob, kPhaseThreads, smem, a_init)) return rc;
@@ -431,7 +436,7 @@ static int phase_host_loop(mpcv_handle* h, cudaStream_t st) {
   for (long sweep = 0; sweep < (long)h->P.max_iter + 2; sweep += chunk) {
     for (int c = 0; c < chunk; ++c) {
       ph_pre_kernel<Model><<<gr.group, kWarpPhaseThreads, smem, st>>>(a);
-      ph_repack_kernel<Model><<<gr.prob, kPhaseThreads, 0, st>>>(a);
+      ph_repack_kernel<Model><<<gr.repack, kPhaseThreads, 0, st>>>(a);
       ph_repack_list_kernel<Model><<<gr.prob, kPhaseThreads, 0, st>>>(a);
       ph_factor_kernel<Model><<<gr.prob, kPhaseThreads, smem, st>>>(a);
       ph_probe_kernel<Model><<<gr.prob, kPhaseThreads, smem, st>>>(a);
