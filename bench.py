@@ -469,7 +469,7 @@ def run_reference(args):
         "config": config_block(wl, args.gpus, {
             "l2": "flushed between steps (256 MB write)", "batches_in_flight": 1 if wl.key == "c1" else max(1, args.inflight),
             "layout": "auto",
-            "parallelism": "problem-index sharding x%d, NCCL all-gather of results + stats (inline)" % args.gpus}),
+            "parallelism": "problem-index sharding x%d, ONE NCCL all-gather of results, statuses and iteration counts per step (inline)" % args.gpus}),
         "cpu_baseline": {"value": value, "unit": "solves/s", "cores": threads, "kind": "port",
                          "sample": "%s x %d steps, %d host threads (CasADi/IPOPT not installable offline; oracle port "
                                    "of IPOPT's algorithm)" % (sample, args.steps, threads)},
@@ -514,11 +514,21 @@ def measure(wl, args, world, rank, dev, gather_mode, steps, warmup, sampler=None
     streams = [main] if F == 1 else [torch.cuda.Stream(dev) for _ in wls]
     flush = [torch.empty(256 * 1024 * 1024 // 8, dtype=torch.float64, device=dev) for _ in streams]   # > 126 MB L2
 
-    def gather(w, outs):
+    # --gather overlap: the collectives of step k run on a high-priority side stream (and NCCL's own high-priority
+    # stream) underneath the solve of step k + 1; the region ends when the last gather has
+    gstream = torch.cuda.Stream(dev, priority=-1) if (world > 1 and gather_mode == "overlap") else None
+
+    def gather(w, outs, overlap=False):
         if world == 1 or gather_mode == "none":
             return None
-        g = [mdist.gather_rows_equal(o.reshape(o.shape[0], -1)) for o in outs]
-        return g, mdist.reduce_stats_device(w.status, w.iters)
+        if overlap and gstream is not None:
+            cur = torch.cuda.current_stream(dev)
+            gstream.wait_stream(cur)
+            with torch.cuda.stream(gstream):
+                for t in list(outs) + [w.status, w.iters]:
+                    t.record_stream(gstream)
+                return mdist.gather_packed(outs, w.status, w.iters)
+        return mdist.gather_packed(outs, w.status, w.iters)
 
     for w, st in zip(wls, streams):
         with torch.cuda.stream(st):
@@ -554,10 +564,12 @@ def measure(wl, args, world, rank, dev, gather_mode, steps, warmup, sampler=None
                 evk[k][0].record()
                 o = w.step()
                 evk[k][1].record()
-                gather(w, o)
+                gather(w, o, overlap=True)
         for st in streams[:lanes]:
             if st is not main:
                 main.wait_stream(st)
+        if gstream is not None:
+            main.wait_stream(gstream)
         t_end.record(main)
         torch.cuda.synchronize()
         if world > 1:
@@ -684,8 +696,9 @@ def main():
                     help="batches in flight: the K steps alternate over this many solver handles / streams.  Measured "
                          "(one B200): C2 15.2 -> 14.5..14.9 ms, C4 98.8 -> 59.4 ms, C4 Frenet 50.8 -> 41.1 ms per step with 2; no "
                          "gain at N > 1, where the NCCL gathers order the streams - so the default stays 1")
-    ap.add_argument("--gather", default="inline", choices=["inline", "none"],
-                    help="N>1: NCCL gather of the results in stream order after each step (none: diagnostic)")
+    ap.add_argument("--gather", default="inline", choices=["inline", "overlap", "none"],
+                    help="N>1: NCCL gather of the results in stream order after each step; overlap: on a high-priority "
+                         "side stream underneath the next step's solve; none: diagnostic")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -702,7 +715,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev, pg_options=opts)
 
     wl = CONFIGS[args.config](batch=args.batch, rank=rank)
     wl.setup(mv, dev, args.layout)
@@ -798,7 +812,7 @@ def main():
         "config": config_block(wl, world, {
             "l2": "flushed between steps (256 MB write)", "batches_in_flight": inflight,
             "layout": {0: "auto", 1: "thread-per-problem", 2: "warp-per-problem", 3: "phase kernels", 4: "CTA-resident"}[args.layout],
-            "parallelism": "problem-index sharding x%d, NCCL all-gather of results + stats (%s)" % (world, args.gather)}),
+            "parallelism": "problem-index sharding x%d, ONE NCCL all-gather of results, statuses and iteration counts per step (%s)" % (world, args.gather)}),
         "e2e": m["e2e"],
         "serial": m["serial"],
         "serial_note": "the same batch with ONE batch in flight (one handle, one stream: the round-1 arrangement)",

@@ -32,8 +32,12 @@ def _worker(rank, world, port, B, out):
     status = torch.zeros(hi - lo, dtype=torch.int32)
     iters = torch.full((hi - lo,), 10 + rank, dtype=torch.int32)
     stats = mdist.reduce_stats(status, iters)
+    # the packed one-collective form of the benchmark (equal shards): same bits, same statistics
+    eq = full[rank * 4:(rank + 1) * 4] * 2.0
+    pk = mdist.gather_packed([eq, eq[:, 0]], torch.zeros(4, dtype=torch.int32), torch.full((4,), 10 + rank, dtype=torch.int32))
     if rank == 0:
-        torch.save({"got": got, "stats": stats}, out)
+        torch.save({"got": got, "stats": stats, "pk_x": pk.outs[0].clone(), "pk_f": pk.outs[1].clone(), "pk_stats": pk.stats(),
+                    "pk_iters": pk.iters.clone()}, out)
     dist.destroy_process_group()
 
 
@@ -50,6 +54,9 @@ def test_gather_and_stats_world_size_2(tmp_path):
     assert torch.equal(r["got"], full)                       # bit-for-bit the single-process result
     assert r["stats"]["problems"] == B and r["stats"]["succeeded"] == B
     assert r["stats"]["iters_sum"] == 5 * 10 + 6 * 11 and r["stats"]["iters_max"] == 11
+    assert torch.equal(r["pk_x"], full[:8]) and torch.equal(r["pk_f"], full[:8, 0])
+    assert r["pk_stats"] == {"problems": 8, "succeeded": 8, "iters_sum": 4 * 10 + 4 * 11, "iters_max": 11}
+    assert r["pk_iters"].tolist() == [10.0] * 4 + [11.0] * 4
 
 
 # ---- T11 on real GPUs: NCCL gather of SOLVER output == the shards solved alone, bit for bit ----------------------
@@ -73,6 +80,7 @@ def _gpu_worker(rank, world, port, B, out):
     st, it = solver._last
     xs, fs = mdist.gather_rows(sol["x"]), mdist.gather_rows(sol["f"])
     stats = mdist.reduce_stats(st, it)
+    pk = mdist.gather_packed([sol["x"], sol["f"]], st, it)        # bench.py's one-collective form (equal shards)
     if rank == 0:
         # every shard once more, alone on this GPU: the multi-GPU plumbing must not change one bit
         alone = []
@@ -80,7 +88,8 @@ def _gpu_worker(rank, world, port, B, out):
             a, b = mdist.shard_range(B, r, world)
             s1 = solver(x0=torch.as_tensor(w0[a:b]).to(dev), lbx=lbx, ubx=ubx, p=torch.as_tensor(p[a:b]).to(dev), outputs=("x", "f"))
             alone.append((s1["x"].clone(), s1["f"].clone(), solver._last[1].clone()))
-        torch.save({"xs": xs.cpu(), "fs": fs.cpu(), "stats": stats,
+        torch.save({"xs": xs.cpu(), "fs": fs.cpu(), "stats": stats, "pk_x": pk.outs[0].cpu(), "pk_f": pk.outs[1].cpu(),
+                    "pk_stats": pk.stats(),
                     "x1": torch.cat([a[0] for a in alone]).cpu(), "f1": torch.cat([a[1] for a in alone]).cpu(),
                     "iters1": int(sum(int(a[2].sum()) for a in alone))}, out)
     dist.destroy_process_group()
@@ -100,3 +109,4 @@ def test_multi_gpu_gather_of_solver_output_is_bit_identical(tmp_path):
     r = torch.load(out)
     assert r["xs"].shape == (B, 53) and torch.equal(r["xs"], r["x1"]) and torch.equal(r["fs"], r["f1"])
     assert r["stats"]["problems"] == B and r["stats"]["succeeded"] == B and r["stats"]["iters_sum"] == r["iters1"]
+    assert torch.equal(r["pk_x"], r["x1"]) and torch.equal(r["pk_f"], r["f1"]) and r["pk_stats"] == r["stats"]
