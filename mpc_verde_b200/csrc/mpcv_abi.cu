@@ -151,6 +151,16 @@ mpcv_handle* mpcv_create(const mpcv_spec* s) {
   }
   h->knobs = mpcv_knobs_from_env();
   cudaGetDevice(&h->device);
+  // Keep the context's local-memory pool at its high-water mark.  The one-kernel layouts carry 0.7 - 1.2 KB stack
+  // frames per thread; without this flag the driver shrinks and regrows the pool around launches of kernels with
+  // smaller frames once such a kernel has run, and a closed loop (hundreds of short launches) that follows a
+  // single-shooting solve in the same process ran 50 % slower (C4 after C1: 153 ms against 100 ms).
+  {
+    unsigned flags = 0;
+    if (cudaGetDeviceFlags(&flags) == cudaSuccess && !(flags & cudaDeviceLmemResizeToMax))
+      cudaSetDeviceFlags(flags | cudaDeviceLmemResizeToMax);
+    cudaGetLastError();
+  }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, h->device) != cudaSuccess) { mpcv_set_error(-EIO, "cudaGetDeviceProperties"); delete h; return nullptr; }
   h->sm_count = prop.multiProcessorCount;
