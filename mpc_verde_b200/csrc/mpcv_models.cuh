@@ -102,6 +102,7 @@ struct Unicycle {
   static constexpr int NPS = (KIND == 2) ? 5 : 0;
   static constexpr bool HAS_UPREV = false;
   static constexpr bool LTI = false;
+  static constexpr int DER_MINB = 4;      // CTAs per SM of the phase pipeline's derivative sweep (register cap 128)
   static constexpr int MODEL_ID = KIND == 0 ? MPCV_MODEL_UNICYCLE_RK4_QUAD
                                 : KIND == 1 ? MPCV_MODEL_UNICYCLE_EULER_NODE
                                             : MPCV_MODEL_UNICYCLE_RK4_NODE;
@@ -325,6 +326,7 @@ struct Linear {
   static constexpr bool HAS_UPREV = DU;
   // (A, B) come from the problem's parameters and the cost Hessian from the weights: the same for every stage
   static constexpr bool LTI = true;
+  static constexpr int DER_MINB = 4;
   static constexpr int MODEL_ID = NXP == 3 ? (DU ? MPCV_MODEL_LINEAR3_DU : MPCV_MODEL_LINEAR3)
                                            : (DU ? MPCV_MODEL_LINEAR4_DU : MPCV_MODEL_LINEAR4);
 
@@ -471,6 +473,7 @@ struct FrenetBicycle {
   static constexpr int NPG = 0, NPS = 4;
   static constexpr bool HAS_UPREV = true;
   static constexpr bool LTI = false;
+  static constexpr int DER_MINB = 1;
   static constexpr int MODEL_ID = MPCV_MODEL_FRENET_BICYCLE;
 
   template <class PS>

@@ -728,8 +728,17 @@ __global__ void __launch_bounds__(kWarpPhaseThreads) ph_slow_kernel(const __grid
   }
 }
 
+// Register cap of the derivative sweep (CTAs per SM it is compiled for, Model::DER_MINB).  The unicycle sweep wants
+// 162 registers (3 CTAs per SM: 2.6 warps per scheduler, FP64 pipe 59 % busy, profiles/r2h_full_metrics.csv); capped at
+// 128 it spills 132 bytes and runs 4 CTAs per SM — same box, C2 per batch: 15.0 - 15.3 ms uncapped, 14.4 at 128
+// registers, 15.0 - 15.6 at 96 (416 bytes of spills).  The Frenet jets already spill at 255: no cap.
+#ifdef MPCV_DER_MINB
+#define MPCV_DER_MINB_OF(Model) MPCV_DER_MINB
+#else
+#define MPCV_DER_MINB_OF(Model) Model::DER_MINB
+#endif
 template <class Model>
-__global__ void __launch_bounds__(kPhaseThreads) ph_der_kernel(const __grid_constant__ PhaseArgs a) {
+__global__ void __launch_bounds__(kPhaseThreads, MPCV_DER_MINB_OF(Model)) ph_der_kernel(const __grid_constant__ PhaseArgs a) {
   double* const slab = a.slab[ph_cur_after_repack(a.ctrl)];
   const int out = (a.ctrl->sweep & 1) ^ 1;
   const long n = a.ctrl->n_act[out], items = n * a.L.N;
