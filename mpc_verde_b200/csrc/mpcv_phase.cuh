@@ -186,6 +186,20 @@ struct Phase {
     ws[L.st + kSlotDwHint] = dw;          // > 0: done, ph_retry_kernel skips it
     ipm.riccati_forward(L.c);
   }
+  // the same on ALL lanes of the winner's probe group: the lane-parallel factorisation and forward sweep
+  // (riccati_factor_lanes: two short steps per stage with the operands exchanged through the dead step buffers, bit
+  // for bit the register form) instead of one lane redoing ~350 dependent instructions per stage while its three
+  // neighbours wait                                                               (LANES lanes per problem)
+  MPCV_HD static void apply_lanes_body(const Params& P, const Layout& L, WS ws, const SolveIO& io, const BndEntry* tab,
+                                       Grp<LANES> g, double dw) {
+    IpmT ipm = make_ipm<IpmT>(P, L, ws, g, io, tab);
+    if (!ipm.template riccati_factor_x<true>(dw, false, 0, L.c)) {
+      if (g.lane == 0) ws[L.st + kSlotDwHint] = -dw;
+      return;
+    }
+    if (g.lane == 0) { ws[L.st + 6] = dw; ws[L.st + kSlotDwHint] = dw; }
+    ipm.riccati_forward(L.c);
+  }
   // inertia-correction retries for the problems the probe could not settle: walk on through the schedule
   // sequentially, then the vector sweeps                                          (thread per problem)
   MPCV_HD static void retry_body(const Params& P, const Layout& L, WS ws, const SolveIO& io, long b,
@@ -530,6 +544,9 @@ __global__ void __launch_bounds__(kPhaseThreads, 4) ph_factor_kernel(const __gri
   }
 }
 
+#ifndef MPCV_PROBE_LANES
+#define MPCV_PROBE_LANES 0   /* 1: the probe's winner redoes its factorisation on all four lanes of the group (apply_lanes_body) instead of one; same box, C2 per batch, five processes each: 14.1 - 14.6 ms (0) against 15.0 - 16.3 (1) — the exchanges go through the slab here, not through shared memory */
+#endif
 // probe: kProbe lanes per problem of the retry list, each trying one element of the delta_w sequence
 template <class Model>
 __global__ void __launch_bounds__(kPhaseThreads, 4) ph_probe_kernel(const __grid_constant__ PhaseArgs a) {
@@ -557,7 +574,11 @@ __global__ void __launch_bounds__(kPhaseThreads, 4) ph_probe_kernel(const __grid
     // the winning lane repeats its factorisation with stores (operands are in L1/L2 now) and runs the vector
     // sweeps; only when none of the probed values worked the problem is left to ph_retry_kernel.  (Handing the
     // stored factorisation to a thread-per-problem launch over the retry list instead: 17.4 -> 17.9 ms.)
+#if MPCV_PROBE_LANES
+    if (it < items && m) Phase<Model, WsStrided, NP>::apply_lanes_body(a.P, a.L, ws, io, tab, Grp<NP>((int)lane), dsel);
+#else
     if (it < items && m && attempt == first) Phase<Model, WsStrided>::apply_body(a.P, a.L, ws, io, tab, dsel);
+#endif
     if (it < items && !m && attempt == 0) ws[a.L.st + kSlotDwHint] = -dsel;
   }
 }
