@@ -692,10 +692,14 @@ def main():
     ap.add_argument("--layout", type=int, default=S.LAYOUT_AUTO)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="do not attach short runs of the other configurations")
-    ap.add_argument("--inflight", type=int, default=1,
-                    help="batches in flight: the K steps alternate over this many solver handles / streams.  Measured "
-                         "(one B200): C2 15.2 -> 14.5..14.9 ms, C4 98.8 -> 59.4 ms, C4 Frenet 50.8 -> 41.1 ms per step with 2; no "
-                         "gain at N > 1, where the NCCL gathers order the streams - so the default stays 1")
+    ap.add_argument("--inflight", type=int, default=2,
+                    help="batches in flight: the K steps alternate over this many solver handles / streams, so that the "
+                         "sparse end of one batch (late sweeps, straggler tail: one warp busy) runs underneath the dense "
+                         "sweeps of the next.  Measured: one B200, C2 15.2 -> 14.5..14.9 ms per step, C4 98.8 -> 59.4; four "
+                         "B200s, where rank 2's batch holds a 119-iteration problem (856 backtracking steps, 311 second-"
+                         "order corrections: a 5 ms tail on one warp that every rank waits for at the gather): 20.9..28.6 -> "
+                         "14.3..14.4 ms per step.  1 = one batch at a time (the round-1 arrangement; reported beside the "
+                         "headline as `serial`).  The single-problem latency config c1 always runs 1")
     ap.add_argument("--gather", default="inline", choices=["inline", "overlap", "none"],
                     help="N>1: NCCL gather of the results in stream order after each step; overlap: on a high-priority "
                          "side stream underneath the next step's solve; none: diagnostic")
