@@ -615,8 +615,11 @@ def measure(wl, args, world, rank, dev, gather_mode, steps, warmup, sampler=None
     e2e_steps = max(3, min(steps, 5)) * F
     pools = [ThreadPoolExecutor(1) for _ in wls]
 
-    def host_job(w, st):
+    def host_job(w, st, k):
         with torch.cuda.device(dev), torch.cuda.stream(st):
+            if not os.environ.get("BENCH_NO_FLUSH"):
+                flush[k % F].fill_(float(k))                 # the same L2 eviction as in the device-timed region
+                st.synchronize()
             res = w.host_step()
             if world > 1 and gather_mode != "none":
                 res = [r.to(dev, non_blocking=True) for r in res]      # (the page-locked result arrays are reused)
@@ -626,7 +629,7 @@ def measure(wl, args, world, rank, dev, gather_mode, steps, warmup, sampler=None
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    futs = [pools[k % F].submit(host_job, wls[k % F], streams[k % F]) for k in range(e2e_steps)]
+    futs = [pools[k % F].submit(host_job, wls[k % F], streams[k % F], k) for k in range(e2e_steps)]
     for k, fu in enumerate(futs):
         res = fu.result()
         if world > 1 and gather_mode != "none":
