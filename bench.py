@@ -79,10 +79,13 @@ class Workload:
         raise NotImplementedError
 
     # -- device side --
-    def setup(self, mv, dev, layout=S.LAYOUT_AUTO):
+    def setup(self, mv, dev, layout=S.LAYOUT_AUTO, pipes=None):
         import torch
-        self.mv, self.dev, self.torch, self.layout = mv, dev, torch, layout
-        self.solver = mv.nlpsol("solver", "ipopt", self.problem(), dict(OPTS, layout=layout))
+        self.mv, self.dev, self.torch, self.layout, self.pipes = mv, dev, torch, layout, pipes
+        extra = {"layout": layout}
+        if pipes:
+            extra["pipes"] = pipes
+        self.solver = mv.nlpsol("solver", "ipopt", self.problem(), dict(OPTS, **extra))
         self.spec = self.solver.spec
         self._setup_inputs()
 
@@ -468,6 +471,7 @@ def run_reference(args):
         # step (a bounded sample of the workload) is said in cpu_baseline.sample
         "config": config_block(wl, args.gpus, {
             "l2": "flushed between steps (256 MB write)", "batches_in_flight": 1 if wl.key == "c1" else max(1, args.inflight),
+            "pipes_per_batch": args.pipes or (4 if wl.key == "c1" or args.inflight <= 1 else 1 if args.inflight >= 3 else 2),
             "layout": "auto",
             "parallelism": "problem-index sharding x%d, ONE NCCL all-gather of results, statuses and iteration counts per step (inline)" % args.gpus}),
         "cpu_baseline": {"value": value, "unit": "solves/s", "cores": threads, "kind": "port",
@@ -508,7 +512,7 @@ def measure(wl, args, world, rank, dev, gather_mode, steps, warmup, sampler=None
     wls = [wl]
     for _ in range(F - 1):
         w = type(wl)(batch=wl.B, rank=wl.rank)
-        w.setup(wl.mv, dev, wl.layout)
+        w.setup(wl.mv, dev, wl.layout, wl.pipes)
         wls.append(w)
     main = torch.cuda.current_stream(dev)
     streams = [main] if F == 1 else [torch.cuda.Stream(dev) for _ in wls]
@@ -540,7 +544,7 @@ def measure(wl, args, world, rank, dev, gather_mode, steps, warmup, sampler=None
     ok = bool((wl.status == 0).all())
     iters_sum = float(wl.iters.sum().item())
 
-    def timed(n_steps, lanes):
+    def timed(n_steps, lanes, wls=wls):
         """n_steps solves round-robin over the first `lanes` handles / streams; returns (region ms, sum of the
         per-launch durations, flush ms that can be subtracted)"""
         evk = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n_steps)]
@@ -588,9 +592,18 @@ def measure(wl, args, world, rank, dev, gather_mode, steps, warmup, sampler=None
     launches = sum(w.solver.kernel_count() for w in wls) - launches0
     if F > 1:
         tk_ms = t_ms                    # overlapped launches: the average launch duration is the region / K
+        # one batch at a time, on a handle with the library's own pipe count (the in-flight handles run one pipe each)
+        ws = wl
+        if wl.pipes:
+            ws = type(wl)(batch=wl.B, rank=wl.rank)
+            ws.setup(wl.mv, dev, wl.layout, None)
+            for _ in range(3):
+                gather(ws, ws.step())
+            torch.cuda.synchronize()
         s_steps = max(3, min(steps, 5))
-        s_ms, sk_ms, _ = timed(s_steps, 1)
+        s_ms, sk_ms, _ = timed(s_steps, 1, [ws])
         serial = {"ms_per_step": s_ms / s_steps, "kernel_ms": sk_ms / s_steps, "steps": s_steps}
+        del ws
     else:
         serial = None
     print("rank %d [%s]: %.3f ms per step in the timed region (%d in flight), %.3f ms per solve launch%s" %
@@ -695,14 +708,18 @@ def main():
     ap.add_argument("--layout", type=int, default=S.LAYOUT_AUTO)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="do not attach short runs of the other configurations")
-    ap.add_argument("--inflight", type=int, default=2,
-                    help="batches in flight: the K steps alternate over this many solver handles / streams, so that the "
-                         "sparse end of one batch (late sweeps, straggler tail: one warp busy) runs underneath the dense "
-                         "sweeps of the next.  Measured: one B200, C2 15.2 -> 14.5..14.9 ms per step, C4 98.8 -> 59.4; four "
-                         "B200s, where rank 2's batch holds a 119-iteration problem (856 backtracking steps, 311 second-"
-                         "order corrections: a 5 ms tail on one warp that every rank waits for at the gather): 20.9..28.6 -> "
-                         "14.3..14.4 ms per step.  1 = one batch at a time (the round-1 arrangement; reported beside the "
-                         "headline as `serial`).  The single-problem latency config c1 always runs 1")
+    ap.add_argument("--inflight", type=int, default=4,
+                    help="batches in flight: the K steps alternate over this many solver handles / streams.  Batches in "
+                         "flight sit in different phases of the solve (a DRAM-bound Riccati sweep of one under the FP64-bound "
+                         "derivative sweep of another, the one-warp straggler tail of one under the dense sweeps of the "
+                         "next), which the lock-step pipes of ONE batch cannot.  Measured on one B200, C2, ms per batch "
+                         "(in flight x pipes per batch): 1x4 14.1..15.0, 2x2 12.1..12.5, 3x1 11.75, 4x1 11.5..11.8, 8x1 "
+                         "11.5; four B200s with rank 2's 119-iteration straggler: 1x4 20.9..28.6, 2x4 14.3.  1 = one batch at "
+                         "a time (the round-1 arrangement; measured in the same run and reported as `serial`).  The single-"
+                         "problem latency config c1 always runs 1")
+    ap.add_argument("--pipes", type=int, default=0,
+                    help="pipes per batch (mpcv_set_knob phase_pipes); 0 = 1 pipe when 3 or more batches are in flight, 2 "
+                         "with two, the library default (4) with one")
     ap.add_argument("--gather", default="inline", choices=["inline", "overlap", "none"],
                     help="N>1: NCCL gather of the results in stream order after each step; overlap: on a high-priority "
                          "side stream underneath the next step's solve; none: diagnostic")
@@ -725,10 +742,13 @@ def main():
         opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev, pg_options=opts)
 
+    def pipes_for(f):
+        return args.pipes or (1 if f >= 3 else 2 if f == 2 else None)
+
     wl = CONFIGS[args.config](batch=args.batch, rank=rank)
-    wl.setup(mv, dev, args.layout)
-    sampler = ClockSampler(local) if rank == 0 and not os.environ.get("BENCH_NO_SAMPLER") else None
     inflight = 1 if wl.key == "c1" else max(1, args.inflight)
+    wl.setup(mv, dev, args.layout, pipes_for(inflight))
+    sampler = ClockSampler(local) if rank == 0 and not os.environ.get("BENCH_NO_SAMPLER") else None
     m = measure(wl, args, world, rank, dev, args.gather, args.steps, args.warmup, sampler, with_latency=True,
                 inflight=inflight)
     assert m["ok"], "solver failures in the benchmark batch"
@@ -749,10 +769,11 @@ def main():
                 continue
             try:
                 w2 = CONFIGS[key](rank=rank)
-                w2.setup(mv, dev, S.LAYOUT_AUTO)
                 f2 = 1 if key == "c1" else max(1, args.inflight)
+                w2.setup(mv, dev, S.LAYOUT_AUTO, pipes_for(f2))
                 m2 = measure(w2, args, world, rank, dev, args.gather, 2 * f2, 3, inflight=f2)
-                o = {"config": config_block(w2, world, {"batches_in_flight": f2}), "value": m2["value"], "unit": "solves/s",
+                o = {"config": config_block(w2, world, {"batches_in_flight": f2, "pipes_per_batch": pipes_for(f2) or 4}),
+                     "value": m2["value"], "unit": "solves/s",
                      "ms_per_step": m2["ms_per_step"], "serial": m2["serial"],
                      "all_succeeded": m2["ok"], "mean_ipm_iters": m2["iters_sum"] / m2["n_solves"], "e2e": m2["e2e"],
                      "gpu_launches": m2["launches"], "roofline": roofline_of(w2, m2, peak_tf, hbm_peak, hbm_src)}
@@ -818,11 +839,12 @@ def main():
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": config_block(wl, world, {
             "l2": "flushed between steps (256 MB write)", "batches_in_flight": inflight,
+            "pipes_per_batch": pipes_for(inflight) or 4,
             "layout": {0: "auto", 1: "thread-per-problem", 2: "warp-per-problem", 3: "phase kernels", 4: "CTA-resident"}[args.layout],
             "parallelism": "problem-index sharding x%d, ONE NCCL all-gather of results, statuses and iteration counts per step (%s)" % (world, args.gather)}),
         "e2e": m["e2e"],
         "serial": m["serial"],
-        "serial_note": "the same batch with ONE batch in flight (one handle, one stream: the round-1 arrangement)",
+        "serial_note": "the same batch with ONE batch in flight (one handle with the library's default four pipes, one stream: the round-1 arrangement)",
         "gpu_launches": m["launches"],
         "clocks": sampler.summary() if sampler is not None else None,
         "roofline": roofline_of(wl, m, peak_tf, hbm_peak, hbm_src),

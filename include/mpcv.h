@@ -302,6 +302,18 @@ int64_t mpcv_launch_count(const mpcv_handle* h);
    graph-driven sweep (which mpcv_launch_count cannot see from the host).  Either out may be NULL. */
 int mpcv_phase_sweeps(mpcv_handle* h, int32_t* sweeps, int64_t* kernel_nodes, void* stream);
 
+/* Execution knobs of a handle, to be set before its first solve (-EBUSY afterwards); the MPCV_* environment variables
+   of DESIGN.md set the same values for every handle of the process.
+     "phase_pipes"     1..8   independent pipes a batch is split into (default 4, never below phase_pipe_min problems
+                              per pipe).  A caller that keeps several batches in flight on several handles wants 1: the
+                              batches then sit in different phases and share the GPU better than the lock-step pipes of
+                              one batch (C2, 4 in flight: 11.5 ms per batch with 1 pipe, 12.0 with 2; one batch alone
+                              with 4 pipes: 14.1).
+     "phase_pipe_min"  >= 32  smallest share of a pipe
+     "tail_below", "tail_shift"   hand-off of the sweeps to the straggler tail at min(B >> shift, below) active problems
+     "resident_below"  AUTO layout: batches smaller than this run in the CTA-resident kernel */
+int mpcv_set_knob(mpcv_handle* h, const char* name, int64_t value);
+
 /* Diagnostic counters accumulated by the kernels since the handle was created (synchronises the device):
    counters4[0] = filter overflows.  IPOPT's line-search filter (the reference's solver, IpFilter.cpp) is unbounded;
    the device filter holds 16 entries after IPOPT's own pruning of dominated entries and drops the oldest when full.

@@ -32,6 +32,7 @@ SIGNATURES = {
     "mpcv_set_latency_buffer": (C.c_int, [_V, _V]),
     "mpcv_launch_count": (C.c_int64, [_V]),
     "mpcv_diag": (C.c_int, [_V, C.POINTER(C.c_uint64)]),
+    "mpcv_set_knob": (C.c_int, [_V, C.c_char_p, C.c_int64]),
     "mpcv_c2d": (C.c_int, [C.c_int32, C.c_int32, C.c_double, _V, _V, _V, _V, C.c_int64, _V]),
     "mpcv_phase_sweeps": (C.c_int, [_V, C.POINTER(C.c_int32), C.POINTER(C.c_int64), _V]),
     "mpcv_closed_loop_ex": (C.c_int, [_V, _V, C.c_int64, _V]),

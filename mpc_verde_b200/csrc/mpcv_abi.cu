@@ -200,6 +200,19 @@ void mpcv_destroy(mpcv_handle* h) {
   delete h;
 }
 
+int mpcv_set_knob(mpcv_handle* h, const char* name, int64_t value) {
+  if (!h || !name) return mpcv_set_error(-EINVAL, "mpcv_set_knob: null argument");
+  if (h->phase) return mpcv_set_error(-EBUSY, "mpcv_set_knob: the handle has laid out its pipes already (set knobs before the first solve)");
+  const std::string n(name);
+  if (n == "phase_pipes") { if (value < 1 || value > 8) return mpcv_set_error(-EINVAL, "phase_pipes: 1..8"); h->knobs.pipes = (int)value; }
+  else if (n == "phase_pipe_min") { if (value < 32) return mpcv_set_error(-EINVAL, "phase_pipe_min: >= 32"); h->knobs.pipe_min = (long)value; }
+  else if (n == "tail_below") h->knobs.tail_cap = (int)value;
+  else if (n == "tail_shift") h->knobs.tail_shift = (int)value;
+  else if (n == "resident_below") h->knobs.resident_below = (long)value;
+  else return mpcv_set_error(-EINVAL, "mpcv_set_knob: unknown knob " + n);
+  return 0;
+}
+
 int mpcv_diag(mpcv_handle* h, uint64_t* counters4) {
   if (!h || !counters4) return mpcv_set_error(-EINVAL, "mpcv_diag: null argument");
   if (cudaDeviceSynchronize() != cudaSuccess ||

@@ -74,8 +74,18 @@ class NlpSolver:
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         with torch.cuda.device(self.device):
             self._handle = _Handle(spec)
+        # execution knobs (include/mpcv.h, mpcv_set_knob): e.g. {"pipes": 1} for a caller that keeps several batches in
+        # flight on several solvers
+        for key, knob in (("pipes", "phase_pipes"), ("pipe_min", "phase_pipe_min"), ("tail_below", "tail_below"),
+                          ("tail_shift", "tail_shift"), ("resident_below", "resident_below")):
+            if opts and key in opts:
+                self.set_knob(knob, opts[key])
         self._last = None
         self._latency = None
+
+    def set_knob(self, name, value):
+        """`mpcv_set_knob`: execution knobs of this solver's handle; before its first solve."""
+        _lib.check(self._handle.lib.mpcv_set_knob(self._handle.h, name.encode(), int(value)), "mpcv_set_knob")
 
     # -- sizes ---------------------------------------------------------------------------
     @property
