@@ -68,6 +68,9 @@ class Workload:
     workload = ""
     flop_per_iter = 0.0           # ALGORITHMIC FLOPs per IPM iteration
     closed_loop = False
+    # batches in flight when --inflight is left at 0: 4 where stragglers / latency-bound closed loops leave the GPU
+    # idle (C2, C4), 1 for the HBM-bound linear configurations (C3: 138 ms one at a time, 143 with four in flight)
+    default_inflight = 4
 
     def __init__(self, batch=None, rank=0):
         self.rank = rank
@@ -156,6 +159,7 @@ class C2(Workload):
 
 
 class C3(C2):
+    default_inflight = 1
     key, index, default_batch = "c3", 2, 262144
     workload = ("C3 cart-pendulum (linear, Du cost R1=1e-4, Q=(1.44,0,1,0)) N=40 T=0.01 RK4-of-linear, |u|<=200, "
                 "set-point x=10, cold start")
@@ -292,6 +296,7 @@ class C4F(LoopWorkload):
 
 
 class C5(LoopWorkload):
+    default_inflight = 1
     key, index, default_batch, n_steps = "c5", 4, 131072, 2
     workload = ("C5 dynamic bicycle (m=1200,a=1.5,b=2,Ca=55000,Jz=1350; A34 as written) N=50 T=0.05, LTV in v_ref[t]~U[0.4,0.8] "
                 "with exact ZOH per scenario and step on the device, Q=I R=1, |delta|<=20, (y,phi) references from "
@@ -341,6 +346,7 @@ class C5(LoopWorkload):
 
 
 class C1(LoopWorkload):
+    default_inflight = 1
     key, index, default_batch, n_steps = "c1", 0, 1, 100
     workload = ("C1 unicycle single shooting, Euler, N=10 T=0.2, (0,0,0)->(10,10,0), the script's own closed loop "
                 "(84 MPC steps, its scrambled warm start), ONE problem: latency pair GPU / CPU")
@@ -463,6 +469,7 @@ def run_reference(args):
             _, _, r = wl.cpu_sample(n, threads)
         dt = (time.perf_counter() - t0) / args.steps
         value, sample, iters = n / dt, "%d problems per step" % n, float(r["iters"].mean())
+    ref_f = 1 if wl.key == "c1" else (args.inflight if args.inflight > 0 else wl.default_inflight)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
@@ -470,8 +477,8 @@ def run_reference(args):
         # the same keys and values as the GPU arm's line for this configuration; what the CPU arm actually ran per
         # step (a bounded sample of the workload) is said in cpu_baseline.sample
         "config": config_block(wl, args.gpus, {
-            "l2": "flushed between steps (256 MB write)", "batches_in_flight": 1 if wl.key == "c1" else max(1, args.inflight),
-            "pipes_per_batch": args.pipes or (4 if wl.key == "c1" or args.inflight <= 1 else 1 if args.inflight >= 3 else 2),
+            "l2": "flushed between steps (256 MB write)", "batches_in_flight": ref_f,
+            "pipes_per_batch": args.pipes or (4 if ref_f <= 1 else 1 if ref_f >= 3 else 2),
             "layout": "auto",
             "parallelism": "problem-index sharding x%d, ONE NCCL all-gather of results, statuses and iteration counts per step (inline)" % args.gpus}),
         "cpu_baseline": {"value": value, "unit": "solves/s", "cores": threads, "kind": "port",
@@ -708,15 +715,16 @@ def main():
     ap.add_argument("--layout", type=int, default=S.LAYOUT_AUTO)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="do not attach short runs of the other configurations")
-    ap.add_argument("--inflight", type=int, default=4,
+    ap.add_argument("--inflight", type=int, default=0,
                     help="batches in flight: the K steps alternate over this many solver handles / streams.  Batches in "
                          "flight sit in different phases of the solve (a DRAM-bound Riccati sweep of one under the FP64-bound "
                          "derivative sweep of another, the one-warp straggler tail of one under the dense sweeps of the "
                          "next), which the lock-step pipes of ONE batch cannot.  Measured on one B200, C2, ms per batch "
                          "(in flight x pipes per batch): 1x4 14.1..15.0, 2x2 12.1..12.5, 3x1 11.75, 4x1 11.5..11.8, 8x1 "
                          "11.5; four B200s with rank 2's 119-iteration straggler: 1x4 20.9..28.6, 2x4 14.3.  1 = one batch at "
-                         "a time (the round-1 arrangement; measured in the same run and reported as `serial`).  The single-"
-                         "problem latency config c1 always runs 1")
+                         "a time (the round-1 arrangement; measured in the same run and reported as `serial`); 0 = the "
+                         "configuration's own default (4 for c2 / c4 / c4f; 1 for the HBM-bound linear c3 / c5 and for the "
+                         "single-problem latency config c1)")
     ap.add_argument("--pipes", type=int, default=0,
                     help="pipes per batch (mpcv_set_knob phase_pipes); 0 = 1 pipe when 3 or more batches are in flight, 2 "
                          "with two, the library default (4) with one")
@@ -746,7 +754,10 @@ def main():
         return args.pipes or (1 if f >= 3 else 2 if f == 2 else None)
 
     wl = CONFIGS[args.config](batch=args.batch, rank=rank)
-    inflight = 1 if wl.key == "c1" else max(1, args.inflight)
+    def inflight_for(w):
+        return 1 if w.key == "c1" else (args.inflight if args.inflight > 0 else w.default_inflight)
+
+    inflight = inflight_for(wl)
     wl.setup(mv, dev, args.layout, pipes_for(inflight))
     sampler = ClockSampler(local) if rank == 0 and not os.environ.get("BENCH_NO_SAMPLER") else None
     m = measure(wl, args, world, rank, dev, args.gather, args.steps, args.warmup, sampler, with_latency=True,
@@ -769,7 +780,7 @@ def main():
                 continue
             try:
                 w2 = CONFIGS[key](rank=rank)
-                f2 = 1 if key == "c1" else max(1, args.inflight)
+                f2 = inflight_for(w2)
                 w2.setup(mv, dev, S.LAYOUT_AUTO, pipes_for(f2))
                 m2 = measure(w2, args, world, rank, dev, args.gather, 2 * f2, 3, inflight=f2)
                 o = {"config": config_block(w2, world, {"batches_in_flight": f2, "pipes_per_batch": pipes_for(f2) or 4}),
