@@ -725,6 +725,9 @@ def main():
                          "a time (the round-1 arrangement; measured in the same run and reported as `serial`); 0 = the "
                          "configuration's own default (4 for c2 / c4 / c4f; 1 for the HBM-bound linear c3 / c5 and for the "
                          "single-problem latency config c1)")
+    ap.add_argument("--seed-rank", type=int, default=None,
+                    help="diagnostic: give this process the synthetic batch of another rank (rank 2's C2 batch holds the "
+                         "119-iteration straggler)")
     ap.add_argument("--pipes", type=int, default=0,
                     help="pipes per batch (mpcv_set_knob phase_pipes); 0 = 1 pipe when 3 or more batches are in flight, 2 "
                          "with two, the library default (4) with one")
