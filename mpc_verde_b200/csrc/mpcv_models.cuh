@@ -103,6 +103,7 @@ struct Unicycle {
   static constexpr bool HAS_UPREV = false;
   static constexpr bool LTI = false;
   static constexpr int DER_MINB = 4;      // CTAs per SM of the phase pipeline's derivative sweep (register cap 128)
+  static constexpr int FAC_MINB = 4;      // ... and of its factor kernel
   static constexpr int MODEL_ID = KIND == 0 ? MPCV_MODEL_UNICYCLE_RK4_QUAD
                                 : KIND == 1 ? MPCV_MODEL_UNICYCLE_EULER_NODE
                                             : MPCV_MODEL_UNICYCLE_RK4_NODE;
@@ -327,6 +328,10 @@ struct Linear {
   // (A, B) come from the problem's parameters and the cost Hessian from the weights: the same for every stage
   static constexpr bool LTI = true;
   static constexpr int DER_MINB = 4;
+  // five states (pendulum with u_prev): at 128 registers the factor kernel spills 1.1 KB per thread; 168 registers
+  // (3 CTAs per SM) cost occupancy this HBM-bound configuration does not need — C3 129 - 136 -> 120 ms per step.  Four
+  // states (C5): no difference (44.3 / 44.1 ms).
+  static constexpr int FAC_MINB = NX >= 5 ? 3 : 4;
   static constexpr int MODEL_ID = NXP == 3 ? (DU ? MPCV_MODEL_LINEAR3_DU : MPCV_MODEL_LINEAR3)
                                            : (DU ? MPCV_MODEL_LINEAR4_DU : MPCV_MODEL_LINEAR4);
 
@@ -474,6 +479,7 @@ struct FrenetBicycle {
   static constexpr bool HAS_UPREV = true;
   static constexpr bool LTI = false;
   static constexpr int DER_MINB = 1;
+  static constexpr int FAC_MINB = 4;
   static constexpr int MODEL_ID = MPCV_MODEL_FRENET_BICYCLE;
 
   template <class PS>

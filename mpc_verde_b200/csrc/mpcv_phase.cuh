@@ -524,8 +524,14 @@ __device__ __forceinline__ int ph_cur_after_repack(const PhaseCtrl* c) {
   return ph_repack_wanted(c, n) ? c->cur ^ 1 : c->cur;
 }
 
+// register cap of the thread-per-problem Riccati kernels (CTAs per SM they are compiled for): Model::FAC_MINB
+#ifdef MPCV_FAC_MINB
+#define MPCV_FAC_MINB_OF(Model) MPCV_FAC_MINB
+#else
+#define MPCV_FAC_MINB_OF(Model) Model::FAC_MINB
+#endif
 template <class Model>
-__global__ void __launch_bounds__(kPhaseThreads, 4) ph_factor_kernel(const __grid_constant__ PhaseArgs a) {
+__global__ void __launch_bounds__(kPhaseThreads, MPCV_FAC_MINB_OF(Model)) ph_factor_kernel(const __grid_constant__ PhaseArgs a) {
   double* const slab = a.slab[ph_cur_after_repack(a.ctrl)];
   const int out = (a.ctrl->sweep & 1) ^ 1;
   const int n = a.ctrl->n_act[out];
