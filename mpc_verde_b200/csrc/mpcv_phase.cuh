@@ -702,9 +702,22 @@ __global__ void __launch_bounds__(kWarpPhaseThreads, MPCV_GROUP_MINB) ph_accept_
 // the sweeps read afterwards (slow) or nothing at all (tail: the problem is finished and exported from the row).
 // (generic addressing on purpose: with __builtin_assume(__isShared(p)) nvcc 12.9 miscompiles the 32-lane phase
 // bodies — the same source on generic pointers is bit-identical to the run on the slab)
+// Guard: tests/test_gpu_parity.py::test_warp_kernels_on_shared_rows_equal_the_slab_run (staged run == run on the slab,
+// bit for bit).  -DMPCV_WSSHARED_ASSUME=1 (scripts/build_variant.sh as 0 -DMPCV_WSSHARED_ASSUME=1) puts the assumption
+// back: round 1's code failed 750 of 1,024 tail problems with it (nvcc 12.9.86, sm_100a); on the end-of-round code
+// (lane-parallel Riccati in the 32-lane bodies) that build passes the guard test — the assumption stays off all the
+// same, an LDS instead of a generic load is not worth a latent miscompile.
+#ifndef MPCV_WSSHARED_ASSUME
+#define MPCV_WSSHARED_ASSUME 0
+#endif
 struct WsShared {
   double* row;
-  __device__ __forceinline__ double& operator[](int i) const { return row[i]; }
+  __device__ __forceinline__ double& operator[](int i) const {
+#if MPCV_WSSHARED_ASSUME
+    __builtin_assume(__isShared(row + i));
+#endif
+    return row[i];
+  }
   __device__ __forceinline__ WsShared view(int off) const { return WsShared{row + off}; }
 };
 __device__ __forceinline__ void ph_cp_async8(double* dst_smem, const double* src) {
