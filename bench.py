@@ -330,8 +330,8 @@ class C5(LoopWorkload):
         return self.solver.closed_loop(d["x_init"], None, d["ptraj"], self.lbx, self.ubx, n_steps=self.n_steps,
                                        warm_mode=S.WARM_SHIFT, pglob_traj=pgt)
 
-    def check(self, outs, n=8):
-        # first solve of the loop against the oracle (its closed loop takes a constant model only)
+    def _first_solves(self, n, threads=1):
+        # first solve of every scenario's loop on the oracle (its closed loop takes a constant model only)
         from oracle import mpc_oracle
         n = min(n, self.B)
         sp = self.spec
@@ -341,8 +341,19 @@ class C5(LoopWorkload):
             A, Bd = problems.c2d(*problems.dynamic_bicycle_matrices(vv), sp.T)
             AB.append(np.concatenate([A.ravel(), Bd.ravel()]))
         p = np.concatenate([x0, np.array(AB), self.host_in["ptraj"][:n, :sp.N].reshape(n, -1)], 1)
-        r = mpc_oracle.solve(sp, problems.cold_start(sp, x0), self.lbx, self.ubx, p)
-        return float(np.abs(outs[0][:n, 0, 0].cpu().numpy() - r["x"][:, sp.nx]).max())
+        w0 = problems.cold_start(sp, x0)
+        t0 = time.perf_counter()
+        r = mpc_oracle.solve(sp, w0, self.lbx, self.ubx, p, nthreads=threads)
+        return n, time.perf_counter() - t0, r
+
+    def cpu_first_solves(self, n, threads):
+        """CPU arm of this configuration: the oracle on the first (cold) solve of n scenarios, all host threads"""
+        self._first_solves(threads, threads)
+        return self._first_solves(n, threads)
+
+    def check(self, outs, n=8):
+        n, _, r = self._first_solves(n)
+        return float(np.abs(outs[0][:n, 0, 0].cpu().numpy() - r["x"][:, self.spec.nx]).max())
 
 
 class C1(LoopWorkload):
@@ -840,6 +851,10 @@ def main():
             from oracle import mpc_oracle
             n = min(wl.B, 16)
             a = wl._oracle_args(n) if hasattr(wl, "_oracle_args") else None
+            if a is None and hasattr(wl, "cpu_first_solves"):
+                n, dt, _ = wl.cpu_first_solves(256 * threads, threads)
+                cpu = {"value": n / dt, "unit": "solves/s", "cores": threads, "kind": "port",
+                       "sample": "first (cold) solve of the loops of %d scenarios, %d host threads, %.1f s wall" % (n, threads, dt)}
             if a is not None:
                 t0 = time.perf_counter()
                 mpc_oracle.closed_loop(wl.spec, *a)
