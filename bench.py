@@ -703,8 +703,16 @@ def roofline_of(wl, m, peak_tf, hbm_peak, hbm_src):
         traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))[wl.key]["dram_bytes_per_step"]
     except Exception:
         pass
+    one = None
+    if m.get("serial"):
+        a1 = flops / (m["serial"]["kernel_ms"] * 1e-3) / 1e12
+        one = {"kernel_ms": m["serial"]["kernel_ms"], "achieved": a1, "frac": a1 / peak_tf}
     return {
         "bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+        # with several batches in flight the launches overlap: kernel_ms is the timed region / K (what one launch costs
+        # the GPU); `one_batch_at_a_time` is the same launch timed alone with CUDA events around it
+        "kernel_ms_is": "timed region / steps" if m.get("inflight", 1) > 1 else "CUDA events around each launch",
+        "one_batch_at_a_time": one,
         "traffic": traffic,
         "traffic_source": "committed ncu capture profiles/r2_traffic.json (not measured in this run)" if traffic else None,
         "peak_source": "FP64 FMA peak measured in this run by mpcv_fp64_peak (MEASURED_PEAKS.json has no FP64 figure)",
