@@ -601,16 +601,10 @@ def measure(wl, args, world, rank, dev, gather_mode, steps, warmup, sampler=None
         flush_ms = sum(a.elapsed_time(b) for a, b in fev) if lanes == 1 else 0.0
         return t_start.elapsed_time(t_end) - flush_ms, sum(a.elapsed_time(b) for a, b in evk), o
 
-    launches0 = sum(w.solver.kernel_count() for w in wls)
-    if sampler is not None:
-        sampler.start()
-    t_ms, tk_ms, outs = timed(steps, F)
-    if sampler is not None:
-        sampler.stop()
-    launches = sum(w.solver.kernel_count() for w in wls) - launches0
+    serial = None
     if F > 1:
-        tk_ms = t_ms                    # overlapped launches: the average launch duration is the region / K
-        # one batch at a time, on a handle with the library's own pipe count (the in-flight handles run one pipe each)
+        # one batch at a time FIRST (nothing else in flight, no clock sampler running), on a handle with the library's
+        # own pipe count (the in-flight handles run one pipe each); mean over its steps
         ws = wl
         if wl.pipes:
             ws = type(wl)(batch=wl.B, rank=wl.rank)
@@ -622,8 +616,15 @@ def measure(wl, args, world, rank, dev, gather_mode, steps, warmup, sampler=None
         s_ms, sk_ms, _ = timed(s_steps, 1, [ws])
         serial = {"ms_per_step": s_ms / s_steps, "kernel_ms": sk_ms / s_steps, "steps": s_steps}
         del ws
-    else:
-        serial = None
+    launches0 = sum(w.solver.kernel_count() for w in wls)
+    if sampler is not None:
+        sampler.start()
+    t_ms, tk_ms, outs = timed(steps, F)
+    if sampler is not None:
+        sampler.stop()
+    launches = sum(w.solver.kernel_count() for w in wls) - launches0
+    if F > 1:
+        tk_ms = t_ms                    # overlapped launches: the average launch duration is the region / K
     print("rank %d [%s]: %.3f ms per step in the timed region (%d in flight), %.3f ms per solve launch%s" %
           (rank, wl.key, t_ms / steps, F, tk_ms / steps,
            "" if serial is None else "; one batch at a time: %.3f ms per step" % serial["ms_per_step"]), file=sys.stderr)
