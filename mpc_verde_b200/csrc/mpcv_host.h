@@ -33,6 +33,7 @@ struct mpcv_host_xfer {
 // read ONCE, when a handle is created, never on the launch path.  -1 = the compiled-in default.
 struct mpcv_knobs {
   int tail_cap = -1, tail_shift = -1, pipes = -1, warp_staged = -1, res_tail = -1;
+  int grid_pct = 100;   // fixed grids of the phase kernels as a percentage of "fills the GPU once"
   long pipe_min = -1, resident_below = -1;
   bool hostloop = false;
 };
@@ -44,6 +45,7 @@ inline mpcv_knobs mpcv_knobs_from_env() {
   if (const char* env = getenv("MPCV_PHASE_PIPE_MIN")) { const long v = atol(env); if (v >= 32) k.pipe_min = v; }
   if (const char* env = getenv("MPCV_PHASE_HOSTLOOP")) k.hostloop = env[0] == '1';
   if (const char* env = getenv("MPCV_WARP_STAGED")) k.warp_staged = atoi(env) & 3;
+  if (const char* env = getenv("MPCV_GRID_PCT")) { const int v = atoi(env); if (v >= 10 && v <= 400) k.grid_pct = v; }
   if (const char* env = getenv("MPCV_RES_TAIL")) k.res_tail = atoi(env);                 // 0: ph_tail_kernel
   if (const char* env = getenv("MPCV_RESIDENT_BELOW")) k.resident_below = atol(env);     // AUTO: resident below this batch
   return k;

@@ -210,7 +210,12 @@ struct PhaseGrids { unsigned prob, stage, warp, group, repack; };
 static PhaseGrids phase_grids(const mpcv_handle* h) {
   const long cap = h->phase->cap, sm = h->sm_count;
   const long wpb = kWarpPhaseThreads / 32;
-  auto clampu = [](long need, long fill) { return (unsigned)(need < fill ? (need < 1 ? 1 : need) : fill); };
+  const long pct = h->knobs.grid_pct;
+  auto clampu = [pct](long need, long fill) {
+    fill = fill * pct / 100;
+    if (fill < 1) fill = 1;
+    return (unsigned)(need < fill ? (need < 1 ? 1 : need) : fill);
+  };
   PhaseGrids g;
   g.prob = clampu(cap / kPhaseThreads, sm * 4);
   // the repack copy is latency-bound (kRepackSplit threads per survivor, 44 registers): as many CTAs as an SM holds
